@@ -1,0 +1,230 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+Each fixture stores the reference's weights (its own ``state_dict``), the seeded inputs and the
+reference's outputs, so parity tests can replay them anywhere.  The full-shape cfg-3 layer is too
+large to commit (10.7 MB of weights), so that fixture stores only (seed, inputs, outputs, a weight
+checksum): the weights are re-created from the seed by ``nflows_b200`` (whose constructors consume
+the torch CPU RNG in the same order as the reference; checked by tests/test_api_reference_parity.py).
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[:0] = [os.path.join(ROOT, "tests", "_shims"), "/root/reference"]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+from nflows import transforms as T  # noqa: E402
+from nflows.distributions import StandardNormal  # noqa: E402
+from nflows.flows import Flow  # noqa: E402
+from nflows.nn.nets import ResidualNet  # noqa: E402
+from nflows.transforms.splines import rational_quadratic as rq  # noqa: E402
+from nflows.utils import torchutils  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def save(name, obj):
+    path = os.path.join(OUT, name + ".pt")
+    torch.save(obj, path)
+    print("{:32s} {:8.1f} KB".format(name, os.path.getsize(path) / 1024))
+
+
+def weight_checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+
+
+def perturb(flow, seed=2):
+    """SURVEY.md section 8d 'well-conditioned perturbed variant'."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in flow.named_parameters():
+            if name.endswith("lower_entries") or name.endswith("upper_entries"):
+                d = (1 + int(np.sqrt(1 + 8 * p.numel()))) // 2
+                p.add_((0.1 / np.sqrt(d)) * torch.randn(p.shape, generator=g))
+            elif name.split(".")[-1] in ("log_scale", "shift", "unconstrained_upper_diag") or (
+                    name.endswith(".bias") and "transform_net" not in name):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            elif "final_layer" in name:
+                p.mul_(3.0)
+
+
+def nsf(features, hidden, layers, num_bins=8, tail_bound=3.0, num_blocks=2):
+    ts = []
+    for i in range(layers):
+        ts.append(T.ActNorm(features))
+        ts.append(T.CompositeTransform([T.RandomPermutation(features), T.LULinear(features, identity_init=True)]))
+        ts.append(T.PiecewiseRationalQuadraticCouplingTransform(
+            mask=torchutils.create_alternating_binary_mask(features, even=(i % 2 == 0)),
+            transform_net_create_fn=lambda i_, o_: ResidualNet(i_, o_, hidden_features=hidden, num_blocks=num_blocks),
+            num_bins=num_bins, tails="linear", tail_bound=tail_bound))
+    return Flow(T.CompositeTransform(ts), StandardNormal([features]))
+
+
+@torch.no_grad()
+def main():
+    # ---- g_searchsorted: reference known-answer (tests/utils/torchutils_test.py:80-90) ----------
+    locs = torch.linspace(0, 1, 10)
+    left, right = locs[:-1], locs[1:]
+    mid = (left + right) / 2
+    queries = torch.stack([left, right - 1e-7, mid])
+    save("searchsorted", {
+        "bin_locations": torch.linspace(0, 1, 10),
+        "inputs": queries,
+        "idx": torch.stack([torchutils.searchsorted(torch.linspace(0, 1, 10).repeat(9, 1), v) for v in queries]),
+    })
+
+    # ---- g_spline: function-level vectors, both directions, constrained + linear tails ----------
+    torch.manual_seed(10)
+    n, k = 4096, 8
+    uw, uh = torch.randn(n, k) * 2, torch.randn(n, k) * 2
+    ud_t, ud_c = torch.randn(n, k - 1) * 2, torch.randn(n, k + 1) * 2
+    ud_t[:16] = 25.0  # softplus linear branch (threshold 20)
+    ud_t[16:32] = -30.0
+    x_t = torch.randn(n) * 2.2
+    b = 3.0
+    x_t[:8] = torch.tensor([-b, b, np.nextafter(np.float32(b), np.float32(4)), np.nextafter(np.float32(-b), np.float32(-4)),
+                            np.nextafter(np.float32(b), np.float32(0)), 0.0, float("nan"), 1e30])
+    x_c = torch.rand(n)
+    x_c[:3] = torch.tensor([0.0, 1.0, 0.5])
+    fx = {}
+    for inv in (False, True):
+        y, l = rq.unconstrained_rational_quadratic_spline(x_t.clone(), uw.clone(), uh.clone(), ud_t.clone(), inverse=inv,
+                                                          tails="linear", tail_bound=b)
+        fx["tails_inv%d" % inv] = (y, l)
+        y, l = rq.rational_quadratic_spline(x_c.clone(), uw.clone(), uh.clone(), ud_c.clone(), inverse=inv)
+        fx["constrained_inv%d" % inv] = (y, l)
+        y, l = rq.rational_quadratic_spline(x_c.clone() * 4 - 1, uw.clone(), uh.clone(), ud_c.clone(), inverse=inv,
+                                            left=-1.0, right=3.0, bottom=-1.0, top=3.0,
+                                            min_bin_width=1e-2, min_bin_height=2e-2, min_derivative=5e-2)
+        fx["constrained_box_inv%d" % inv] = (y, l)
+    save("spline", dict(uw=uw, uh=uh, ud_tails=ud_t, ud_constrained=ud_c, x_tails=x_t, x_constrained=x_c,
+                        tail_bound=b, **fx))
+
+    # ---- g_cfg1: 2-layer affine coupling D=2 (BASELINE configs[0]) -------------------------------
+    torch.manual_seed(0)
+    f = lambda i, o: ResidualNet(i, o, hidden_features=8)
+    flow = Flow(T.CompositeTransform([T.AffineCouplingTransform(mask=[1, 0], transform_net_create_fn=f),
+                                      T.AffineCouplingTransform(mask=[0, 1], transform_net_create_fn=f)]),
+                StandardNormal([2])).eval()
+    torch.manual_seed(0)
+    x = torch.randn(1024, 2)
+    z, lad = flow._transform(x)
+    xr, ladr = flow._transform.inverse(z)
+    save("cfg1_affine", dict(sd=flow.state_dict(), x=x, z=z, lad=lad, log_prob=flow.log_prob(x), x_roundtrip=xr,
+                             lad_inverse=ladr))
+
+    # ---- g_affine_general: GENERAL scale activation + additive, D=10 ------------------------------
+    torch.manual_seed(3)
+    f = lambda i, o: ResidualNet(i, o, hidden_features=16)
+    mask = torchutils.create_mid_split_binary_mask(10)
+    tg = T.AffineCouplingTransform(mask, f, scale_activation=T.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION).eval()
+    ta = T.AdditiveCouplingTransform(mask, f).eval()
+    for t in (tg, ta):
+        for name, p in t.named_parameters():
+            if "final_layer" in name or "blocks.1.linear_layers.1" in name:
+                p.mul_(4.0)
+    x = torch.randn(512, 10) * 2
+    yg, lg = tg(x)
+    ya, la = ta(x)
+    save("affine_variants", dict(sd_general=tg.state_dict(), sd_additive=ta.state_dict(), x=x, y_general=yg, lad_general=lg,
+                                 y_additive=ya, lad_additive=la, xinv_general=tg.inverse(x)[0],
+                                 ladinv_general=tg.inverse(x)[1]))
+
+    # ---- g_cfg2: single RQ coupling D=64 K=8 H=128 (BASELINE configs[1]); default and x3 ---------
+    torch.manual_seed(0)
+    t = T.PiecewiseRationalQuadraticCouplingTransform(
+        mask=torchutils.create_alternating_binary_mask(64),
+        transform_net_create_fn=lambda i, o: ResidualNet(i, o, hidden_features=128, num_blocks=2),
+        num_bins=8, tails="linear", tail_bound=3.0).eval()
+    torch.manual_seed(1)
+    x = torch.randn(512, 64)
+    x[0, :8] = torch.tensor([-3.0, 3.0, 3.0000002, -3.0000002, 2.9999998, 0.0, 100.0, -1e-30])
+    out = dict(sd={k: v.clone() for k, v in t.state_dict().items()}, x=x, checksum=weight_checksum(t.state_dict()))
+    out["y"], out["lad"] = t(x)
+    out["xinv"], out["ladinv"] = t.inverse(x)
+    for name, p in t.named_parameters():
+        if "final_layer" in name:
+            p.mul_(3.0)
+    out["y_x3"], out["lad_x3"] = t(x)
+    out["xinv_x3"], out["ladinv_x3"] = t.inverse(x)
+    save("cfg2_rq_coupling", out)
+
+    # ---- g_rq_constrained: tails=None coupling on U[0,1), odd D, K=5, mid-split mask -------------
+    torch.manual_seed(4)
+    t = T.PiecewiseRationalQuadraticCouplingTransform(
+        mask=torchutils.create_mid_split_binary_mask(11),
+        transform_net_create_fn=lambda i, o: ResidualNet(i, o, hidden_features=24, num_blocks=1),
+        num_bins=5, tails=None, min_bin_width=2e-3, min_bin_height=3e-3, min_derivative=4e-3).eval()
+    for name, p in t.named_parameters():
+        if "final_layer" in name:
+            p.mul_(5.0)
+    x = torch.rand(300, 11)
+    y, l = t(x)
+    xi, li = t.inverse(x)
+    save("rq_coupling_constrained", dict(sd=t.state_dict(), x=x, y=y, lad=l, xinv=xi, ladinv=li))
+
+    # ---- g_linear: ActNorm / LULinear / Permutation standalone, D=37 ------------------------------
+    torch.manual_seed(5)
+    d = 37
+    an, lu, pm = T.ActNorm(d).eval(), T.LULinear(d, identity_init=False).eval(), T.RandomPermutation(d).eval()
+    an.log_scale.add_(0.3 * torch.randn(d))
+    an.shift.add_(torch.randn(d))
+    lu.bias.add_(torch.randn(d))
+    x = torch.randn(257, d)
+    rec = dict(x=x, sd_actnorm=an.state_dict(), sd_lu=lu.state_dict(), sd_perm=pm.state_dict())
+    for nm, m in (("actnorm", an), ("lu", lu), ("perm", pm)):
+        rec[nm + "_y"], rec[nm + "_lad"] = m(x)
+        rec[nm + "_xinv"], rec[nm + "_ladinv"] = m.inverse(x)
+    rec["lu_weight"], rec["lu_weight_inverse"], rec["lu_logabsdet"] = lu.weight(), lu.weight_inverse(), lu.logabsdet()
+    save("linear_transforms", rec)
+
+    # ---- g_nsf_small: 3-layer NSF D=24 H=32, perturbed; log_prob + inverse ------------------------
+    torch.manual_seed(0)
+    flow = nsf(24, 32, 3).eval()
+    perturb(flow)
+    torch.manual_seed(1)
+    x = torch.randn(384, 24)
+    z, lad = flow._transform(x)
+    noise = torch.randn(384, 24)
+    xs, lads = flow._transform.inverse(noise)
+    save("nsf_small", dict(sd=flow.state_dict(), x=x, z=z, lad=lad, log_prob=flow.log_prob(x), noise=noise,
+                           sample=xs, lad_inverse=lads, features=24, hidden=32, layers=3))
+
+    # ---- g_nsf784_layer: ONE full-shape cfg-3 layer (D=784 H=256 K=8), weights by seed ------------
+    torch.manual_seed(0)
+    flow = nsf(784, 256, 1).eval()
+    perturb(flow)
+    torch.manual_seed(1)
+    x = torch.randn(96, 784)
+    z, lad = flow._transform(x)
+    xi, li = flow._transform.inverse(x)
+    zd, ladd = flow.double()._transform(x.double())
+    save("nsf784_layer", dict(seed=0, perturb_seed=2, x=x, z=z, lad=lad, log_prob=flow.float().log_prob(x), xinv=xi, ladinv=li,
+                              z_fp64=zd, lad_fp64=ladd, checksum=weight_checksum(flow.float().state_dict()),
+                              features=784, hidden=256, layers=1))
+
+    # ---- g_nsf784_full: the 10-layer cfg-3 flow, 32 rows, weights by seed -------------------------
+    torch.manual_seed(0)
+    flow = nsf(784, 256, 10).eval()
+    perturb(flow)
+    torch.manual_seed(1)
+    x = torch.randn(32, 784)
+    lp = flow.log_prob(x)
+    z = flow.transform_to_noise(x)
+    ck = weight_checksum(flow.state_dict())
+    lpd = flow.double().log_prob(x.double())
+    save("nsf784_full", dict(seed=0, perturb_seed=2, x=x, log_prob=lp, z=z, log_prob_fp64=lpd, checksum=ck,
+                             features=784, hidden=256, layers=10))
+
+
+if __name__ == "__main__":
+    main()
