@@ -1,0 +1,119 @@
+/*
+ * nfk.h -- C ABI of libnfk_sm100.so: the B200 (sm_100a) kernels behind the nflows coupling-flow hot path.
+ *
+ * The reference (bayesiains/nflows) has NO native/FFI layer: its operator API is the Python protocol
+ * `Transform.forward/inverse(inputs, context) -> (outputs, logabsdet)` (nflows/transforms/base.py:22-29).
+ * This header is the boundary a binding for that protocol needs; every entry point cites the reference
+ * code it replaces (paths relative to /root/reference/nflows).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - return 0 on success, a negative NFK_E_* code on failure; nfk_last_error() gives a thread-local message.
+ *   - no allocation, no synchronisation, no stream creation inside: every pointer is caller-owned DEVICE
+ *     memory (fp32, row-major), kernels are enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - `ld*` are row strides in ELEMENTS.  `lad_accum` ([n_rows] fp32) is read-modify-written: the running
+ *     sum of log|det J| that CompositeTransform._cascade (transforms/base.py:44-52) keeps, here on device.
+ *   - `flags` (device int32, may be NULL) is OR-ed with NFK_FLAG_* bits; the host reads it when it wants the
+ *     reference's exceptions (InputOutsideDomain, rational_quadratic.py:81-82; AssertionError, :142).
+ *   - column index lists are int32 device arrays.
+ */
+#ifndef NFK_H_
+#define NFK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFK_ABI_VERSION 1
+
+#define NFK_OK 0
+#define NFK_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
+#define NFK_E_CUDA (-2)      /* CUDA runtime error at launch */
+#define NFK_E_UNSUPPORTED (-3)
+
+#define NFK_FLAG_OUTSIDE_DOMAIN 1  /* constrained spline input outside [left,right] */
+#define NFK_FLAG_NEG_DISCRIMINANT 2 /* inverse spline: b^2-4ac < 0 */
+
+#define NFK_MAX_BINS 64
+
+/* Spline hyper-parameters: kwargs of rational_quadratic_spline / unconstrained_rational_quadratic_spline
+ * (transforms/splines/rational_quadratic.py:13-25, 66-80). */
+typedef struct NfkSplineDesc {
+    int32_t num_bins;        /* K */
+    int32_t linear_tails;    /* 1: tails="linear" (identity outside [-B,B], boundary derivatives padded, ud has K-1
+                                entries); 0: constrained (ud has K+1 entries, domain flag raised outside) */
+    double left, right, bottom, top; /* linear_tails: (-B, B, -B, B) */
+    double min_bin_width, min_bin_height, min_derivative;
+    double softplus_beta;    /* 1.0, or log(2)/(1-min_derivative) when enable_identity_init (:100-104) */
+    double wh_divisor;       /* sqrt(hidden_features) applied to widths/heights (coupling.py:554-559); 1.0 = none */
+} NfkSplineDesc;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int nfk_version(void);
+const char* nfk_last_error(void);
+/* number of kernels this library has enqueued since load (all threads); evidence for bench.py's gpu_launches */
+int64_t nfk_launch_count(void);
+/* 0 if the current device is compute capability 10.x, else NFK_E_UNSUPPORTED */
+int nfk_check_device(void);
+
+/* ---- rational-quadratic spline ------------------------------------------------------------------------- */
+/* Elementwise spline = rational_quadratic_spline / unconstrained_... (rational_quadratic.py:13-181) incl.
+ * torchutils.searchsorted (utils/torchutils.py:134-136).  Element e reads x[e] and parameter row
+ * r = (param_period ? e % param_period : e): uw[r*stride_w + k], uh[r*stride_h + k], ud[r*stride_d + k].
+ * Writes y[e], lad[e].  param_period > 0 gives the batch-shared parameters of PiecewiseRationalQuadraticCDF
+ * (transforms/nonlinearities.py:386-467). */
+int nfk_rqs_elementwise(const NfkSplineDesc* desc, int inverse, const float* x, const float* uw, const float* uh,
+                        const float* ud, int64_t stride_w, int64_t stride_h, int64_t stride_d, int64_t param_period,
+                        float* y, float* lad, int64_t n_elem, int32_t* flags, void* stream);
+
+/* Coupling epilogue with the conditioner output in HBM = PiecewiseCouplingTransform._coupling_transform +
+ * _piecewise_cdf + sum_except_batch + the scatter of CouplingTransform.forward (coupling.py:96-98, 279-293,
+ * 549-582).  params is [n_rows, d_t*M] contiguous, column j*M+k = parameter k of transformed feature j,
+ * M = 3K-1 (tails) or 3K+1.  Feature j is read from x[n*ldx + t_cols[j]] and written to y[n*ldy + t_cols[j]];
+ * the d_id identity columns id_cols are copied bit-exactly.  lad_accum[n] += sum_j lad(n, j). */
+int nfk_rqs_rows(const NfkSplineDesc* desc, int inverse, const float* x, int64_t ldx, const float* params,
+                 const int32_t* t_cols, int32_t d_t, const int32_t* id_cols, int32_t d_id, float* y, int64_t ldy,
+                 float* lad_accum, int64_t n_rows, int32_t* flags, void* stream);
+
+/* ---- dense layers (conditioner ResidualNet/MLP, LULinear, folded ActNorm+Permutation+LU) ------------------ */
+/* Y[n, o] = post( sum_k pre(X[n, k]) * W[o, k] + bias[o] ) + R[n, o]
+ * with pre = relu if relu_in, post = relu if relu_out, R optional (NULL).  W is [out, in] row-major exactly as
+ * torch.nn.Linear stores it (F.linear: nn/nets/resnet.py:44-49,94-99; transforms/lu.py:65-66).  fp32 accumulate
+ * with fp32-equivalent operand precision (SIMT FFMA path, or split-TF32 tcgen05 path). */
+int nfk_linear(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, const float* R,
+               int64_t ldr, float* Y, int64_t ldy, int64_t n_rows, int32_t in_features, int32_t out_features,
+               int relu_in, int relu_out, void* stream);
+
+/* ---- row-wise elementwise transforms -------------------------------------------------------------------- */
+/* out[n, j] = x[n*ldx + cols[j]] (identity_split gather, coupling.py:82; Permutation._permute,
+ * permutations.py:27-39).  Bit-exact copy. */
+int nfk_gather_cols(const float* x, int64_t ldx, const int32_t* cols, int32_t n_cols, float* out, int64_t ldo,
+                    int64_t n_rows, void* stream);
+
+/* ActNorm (transforms/normalization.py:171-204): forward y = scale[j]*x + shift[j]; inverse y = (x - shift[j]) /
+ * scale[j]; scale = exp(log_scale) is computed by the caller.  lad_accum[n] += lad_const (may be NULL/0). */
+int nfk_actnorm(const float* x, int64_t ldx, const float* scale, const float* shift, float* y, int64_t ldy,
+                float* lad_accum, float lad_const, int64_t n_rows, int32_t d, int inverse, void* stream);
+
+/* lad_accum[n] += c for every row (constant log|det| of LULinear / ActNorm, lu.py:123-129). */
+int nfk_add_const(float* lad_accum, float c, int64_t n_rows, void* stream);
+int nfk_fill(float* dst, float value, int64_t n, void* stream);
+
+/* Affine / additive coupling epilogue (coupling.py:212-269).  params is [n_rows, mult*d_t] contiguous with the
+ * BLOCKED layout shift = params[:, :d_t], raw scale = params[:, d_t:] (mult = 2), or shift only (mult = 1,
+ * additive).  scale_activation: 0 = sigmoid(u+2)+1e-3 (DEFAULT), 1 = clamp(softplus(u)+1e-3, 0, 3) (GENERAL). */
+int nfk_affine_coupling_rows(const float* x, int64_t ldx, const float* params, int32_t mult, int32_t scale_activation,
+                             int inverse, const int32_t* t_cols, int32_t d_t, const int32_t* id_cols, int32_t d_id,
+                             float* y, int64_t ldy, float* lad_accum, int64_t n_rows, void* stream);
+
+/* StandardNormal._log_prob + Flow._log_prob's final add (distributions/normal.py:23-33, flows/base.py:49):
+ * out[n] = (-0.5 * sum_j z[n, j]^2 - log_z) + (lad ? lad[n] : 0). */
+int nfk_std_normal_log_prob(const float* z, int64_t ldz, int32_t d, float log_z, const float* lad, float* out,
+                            int64_t n_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFK_H_ */

@@ -1,0 +1,18 @@
+"""nflows_b200: B200-native (sm_100a) implementation of the nflows coupling-flow hot path.
+
+Drop-in for `nflows.transforms.Transform / CompositeTransform`, the coupling / ActNorm / LULinear /
+Permutation transforms, `Flow.log_prob / sample` and `StandardNormal` -- same class names, constructor
+kwargs, state_dict keys and exceptions -- with CUDA fp32 inference executed by hand-written kernels in
+libnfk_sm100.so (C ABI: include/nfk.h)."""
+__version__ = "0.1.0"
+
+
+class _Config:
+    #: read the device flag word after each public call and raise the reference's exceptions
+    #: (InputOutsideDomain / AssertionError).  Costs one device->host sync per call.
+    check_domain = True
+    #: upper bound (MiB) for the conditioner-output chunk a coupling keeps in flight; sized to stay in B200's L2
+    param_chunk_mib = 64
+
+
+config = _Config()

@@ -1,0 +1,123 @@
+"""ctypes binding of libnfk_sm100.so (C ABI: include/nfk.h).
+
+PyTorch is only the plumbing here: it owns device memory and the current CUDA stream; every kernel on
+the hot path is one of ours, reached through this module.  There is NO fallback: if the shared library
+is missing or the device is not sm_100, calls raise.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libnfk_sm100.so")
+_lib = None
+
+
+class NativeUnavailable(RuntimeError):
+    pass
+
+
+class NfkSplineDesc(Structure):
+    _fields_ = [
+        ("num_bins", c_int32), ("linear_tails", c_int32),
+        ("left", c_double), ("right", c_double), ("bottom", c_double), ("top", c_double),
+        ("min_bin_width", c_double), ("min_bin_height", c_double), ("min_derivative", c_double),
+        ("softplus_beta", c_double), ("wh_divisor", c_double),
+    ]
+
+
+_P = c_void_p  # device pointers travel as integers
+
+_SIGNATURES = {
+    "nfk_version": (c_int, []),
+    "nfk_last_error": (c_char_p, []),
+    "nfk_launch_count": (c_int64, []),
+    "nfk_check_device": (c_int, []),
+    "nfk_rqs_elementwise": (c_int, [POINTER(NfkSplineDesc), c_int, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64,
+                                    _P, _P, c_int64, _P, _P]),
+    "nfk_rqs_rows": (c_int, [POINTER(NfkSplineDesc), c_int, _P, c_int64, _P, _P, c_int32, _P, c_int32, _P, c_int64, _P,
+                             c_int64, _P, _P]),
+    "nfk_linear": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int32, c_int32, c_int, c_int,
+                           _P]),
+    "nfk_gather_cols": (c_int, [_P, c_int64, _P, c_int32, _P, c_int64, c_int64, _P]),
+    "nfk_actnorm": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, c_float, c_int64, c_int32, c_int, _P]),
+    "nfk_add_const": (c_int, [_P, c_float, c_int64, _P]),
+    "nfk_fill": (c_int, [_P, c_float, c_int64, _P]),
+    "nfk_affine_coupling_rows": (c_int, [_P, c_int64, _P, c_int32, c_int32, c_int, _P, c_int32, _P, c_int32, _P, c_int64,
+                                         _P, c_int64, _P]),
+    "nfk_std_normal_log_prob": (c_int, [_P, c_int64, c_int32, c_float, _P, _P, c_int64, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises NativeUnavailable when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise NativeUnavailable(
+            "libnfk_sm100.so not found at {}; run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). nflows_b200 has no CPU/PyTorch fallback for CUDA tensors.".format(_LIB_PATH))
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.nfk_version() != 1:
+        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 1".format(lib.nfk_version()))
+    _lib = lib
+    return lib
+
+
+_device_checked = False
+
+
+def lib():
+    """The library, after checking once that the current CUDA device can run it."""
+    global _device_checked
+    l = load()
+    if not _device_checked:
+        if not torch.cuda.is_available():
+            raise NativeUnavailable("nflows_b200 native kernels need a CUDA device (B200, sm_100a)")
+        check(l.nfk_check_device(), l)
+        _device_checked = True
+    return l
+
+
+def check(rc, l=None):
+    if rc != 0:
+        l = l or load()
+        raise RuntimeError("libnfk_sm100: {} (code {})".format(l.nfk_last_error().decode(), rc))
+
+
+def launch_count():
+    return int(load().nfk_launch_count())
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def spline_desc(num_bins, tails, tail_bound, left, right, bottom, top, min_bin_width, min_bin_height, min_derivative,
+                enable_identity_init=False, wh_divisor=1.0):
+    import math
+    if tails is None:
+        lt, l, r, b, t = 0, left, right, bottom, top
+    elif tails == "linear":
+        lt, l, r, b, t = 1, -tail_bound, tail_bound, -tail_bound, tail_bound
+    else:
+        raise RuntimeError("{} tails are not implemented.".format(tails))
+    beta = math.log(2) / (1 - min_derivative) if enable_identity_init else 1.0
+    return NfkSplineDesc(int(num_bins), lt, float(l), float(r), float(b), float(t), float(min_bin_width),
+                         float(min_bin_height), float(min_derivative), float(beta), float(wh_divisor))

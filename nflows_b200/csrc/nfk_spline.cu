@@ -1,0 +1,245 @@
+// Rational-quadratic spline kernels (HBM-bound): the functional elementwise API and the coupling epilogue that
+// consumes conditioner outputs stored in HBM.  See include/nfk.h for the reference lines each one replaces.
+#include <math.h>
+
+#include <algorithm>
+
+#include "nfk_common.cuh"
+#include "rq_spline.cuh"
+
+namespace nfk {
+
+static int make_spline_params(const NfkSplineDesc* d, SplineParams* p) {
+    if (!d) return fail(NFK_E_INVALID, "spline desc is NULL");
+    const int K = d->num_bins;
+    if (K < 1 || K > NFK_MAX_BINS) return fail(NFK_E_INVALID, "num_bins=%d outside [1,%d]", K, NFK_MAX_BINS);
+    // reference raises ValueError for these (rational_quadratic.py:86-89); the host mirror raises before calling.
+    if (d->min_bin_width * K > 1.0) return fail(NFK_E_INVALID, "Minimal bin width too large for the number of bins");
+    if (d->min_bin_height * K > 1.0) return fail(NFK_E_INVALID, "Minimal bin height too large for the number of bins");
+    p->num_bins = K;
+    p->linear_tails = d->linear_tails ? 1 : 0;
+    p->left = (float)d->left; p->right = (float)d->right; p->bottom = (float)d->bottom; p->top = (float)d->top;
+    p->span_w = (float)(d->right - d->left);
+    p->span_h = (float)(d->top - d->bottom);
+    p->min_w = (float)d->min_bin_width; p->min_h = (float)d->min_bin_height; p->min_d = (float)d->min_derivative;
+    p->mix_w = (float)(1.0 - d->min_bin_width * K);
+    p->mix_h = (float)(1.0 - d->min_bin_height * K);
+    p->beta = (float)d->softplus_beta;
+    p->inv_beta = (float)(1.0 / d->softplus_beta);
+    // x /= np.sqrt(H) on a tensor is executed by ATen as x * float(1.0 / float(sqrt(H)))
+    float div = (float)d->wh_divisor;
+    p->pre_scale = (d->wh_divisor == 1.0) ? 1.0f : (float)(1.0 / (double)div);
+    p->edge_ud = (float)log(exp(1.0 - d->min_derivative) - 1.0);
+    p->knot_eps = 1e-6f;
+    return NFK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// elementwise API: one thread per element, parameters read straight from global memory
+// ------------------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(256) rqs_elementwise_kernel(SplineParams p, int inverse, const float* __restrict__ x,
+                                                              const float* __restrict__ uw, const float* __restrict__ uh,
+                                                              const float* __restrict__ ud, int64_t stride_w,
+                                                              int64_t stride_h, int64_t stride_d, int64_t period,
+                                                              float* __restrict__ y, float* __restrict__ lad,
+                                                              int64_t n_elem, int32_t* flags) {
+    const int K = p.num_bins;
+    int flag = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = period > 0 ? e % period : e;
+        float w[KMAX], h[KMAX], d[KMAX + 1];
+        const float* pw = uw + r * stride_w;
+        const float* ph = uh + r * stride_h;
+        const float* pd = ud + r * stride_d;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            w[k] = (k < K) ? __ldg(pw + k) : 0.0f;
+            h[k] = (k < K) ? __ldg(ph + k) : 0.0f;
+        }
+        if (p.linear_tails) {
+#pragma unroll
+            for (int k = 0; k <= KMAX; ++k) d[k] = (k >= 1 && k < K) ? __ldg(pd + k - 1) : p.edge_ud;
+        } else {
+#pragma unroll
+            for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? __ldg(pd + k) : 0.0f;
+        }
+        float yy, ll;
+        rqs_eval<KMAX>(p, inverse != 0, x[e], w, h, d, yy, ll, flag);
+        y[e] = yy;
+        lad[e] = ll;
+    }
+    if (flag && flags) atomicOr(flags, flag);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// coupling epilogue: params [n_rows, d_t*M] in HBM, staged through shared memory in 128-element chunks
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kRowsThreads = 128;
+
+template <int KMAX>
+__global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, int inverse, const float* __restrict__ x,
+                                                                int64_t ldx, const float* __restrict__ params,
+                                                                const int32_t* __restrict__ t_cols, int d_t,
+                                                                const int32_t* __restrict__ id_cols, int d_id,
+                                                                float* __restrict__ y, int64_t ldy,
+                                                                float* __restrict__ lad_accum, int64_t n_rows,
+                                                                int rows_per_group, int32_t* flags) {
+    extern __shared__ __align__(16) float sp[];   // [kRowsThreads * M] staged parameters, then [kRowsThreads] lad
+    const int K = p.num_bins;
+    const int M = p.linear_tails ? 3 * K - 1 : 3 * K + 1;
+    float* s_lad = sp + kRowsThreads * M;
+    const int tid = threadIdx.x;
+    const int64_t n_groups = (n_rows + rows_per_group - 1) / rows_per_group;
+    int flag = 0;
+
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int64_t row0 = g * rows_per_group;
+        const int rows_here = (int)min((int64_t)rows_per_group, n_rows - row0);
+        const int n_el = rows_here * d_t;
+        float my_lad = 0.0f;
+
+        for (int e0 = 0; e0 < n_el; e0 += kRowsThreads) {
+            const int cnt = min(kRowsThreads, n_el - e0);
+            const float* src = params + (row0 * d_t + e0) * (int64_t)M;
+            const int n_f = cnt * M;
+            if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+                const float4* src4 = reinterpret_cast<const float4*>(src);
+                float4* dst4 = reinterpret_cast<float4*>(sp);
+                for (int i = tid; i < (n_f >> 2); i += kRowsThreads) dst4[i] = __ldcs(src4 + i);
+                for (int i = (n_f & ~3) + tid; i < n_f; i += kRowsThreads) sp[i] = __ldcs(src + i);
+            } else {
+                for (int i = tid; i < n_f; i += kRowsThreads) sp[i] = __ldcs(src + i);
+            }
+            __syncthreads();
+            float ll = 0.0f;
+            if (tid < cnt) {
+                const int e = e0 + tid;
+                const int r = e / d_t;
+                const int j = e - r * d_t;
+                const int col = t_cols ? t_cols[j] : j;
+                const int64_t row = row0 + r;
+                const float* q = sp + tid * M;
+                float w[KMAX], h[KMAX], d[KMAX + 1];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    w[k] = (k < K) ? q[k] : 0.0f;
+                    h[k] = (k < K) ? q[K + k] : 0.0f;
+                }
+                if (p.linear_tails) {
+#pragma unroll
+                    for (int k = 0; k <= KMAX; ++k) d[k] = (k >= 1 && k < K) ? q[2 * K + k - 1] : p.edge_ud;
+                } else {
+#pragma unroll
+                    for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? q[2 * K + k] : 0.0f;
+                }
+                float yy;
+                rqs_eval<KMAX>(p, inverse != 0, x[row * ldx + col], w, h, d, yy, ll, flag);
+                y[row * ldy + col] = yy;
+            }
+            if (rows_per_group > 1) s_lad[tid] = ll; else my_lad += ll;
+            __syncthreads();
+        }
+
+        // identity columns: bit-exact copy (coupling.py:96-97)
+        for (int e = tid; e < rows_here * d_id; e += kRowsThreads) {
+            const int r = e / d_id;
+            const int col = id_cols[e - r * d_id];
+            y[(row0 + r) * ldy + col] = x[(row0 + r) * ldx + col];
+        }
+
+        if (lad_accum) {
+            if (rows_per_group > 1) {
+                // single chunk by construction (rows_per_group * d_t <= kRowsThreads): fixed-order per-row sums
+                if (tid < rows_here) {
+                    float s = 0.0f;
+                    for (int j = 0; j < d_t; ++j) s += s_lad[tid * d_t + j];
+                    lad_accum[row0 + tid] += s;
+                }
+                __syncthreads();
+            } else {
+                // deterministic block tree reduction
+                float v = my_lad;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((tid & 31) == 0) s_lad[tid >> 5] = v;
+                __syncthreads();
+                if (tid == 0) {
+                    float s = 0.0f;
+                    for (int w = 0; w < kRowsThreads / 32; ++w) s += s_lad[w];
+                    lad_accum[row0] += s;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (flag && flags) atomicOr(flags, flag);
+}
+
+template <int KMAX>
+static int launch_rows(const SplineParams& p, int inverse, const float* x, int64_t ldx, const float* params,
+                       const int32_t* t_cols, int d_t, const int32_t* id_cols, int d_id, float* y, int64_t ldy,
+                       float* lad_accum, int64_t n_rows, int32_t* flags, cudaStream_t st) {
+    const int K = p.num_bins;
+    const int M = p.linear_tails ? 3 * K - 1 : 3 * K + 1;
+    const size_t smem = (size_t)(kRowsThreads * M + kRowsThreads) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rqs_rows_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    const int rpg = d_t >= kRowsThreads ? 1 : max(1, kRowsThreads / d_t);
+    const int64_t n_groups = (n_rows + rpg - 1) / rpg;
+    const int grid = (int)std::min<int64_t>(n_groups, 148 * 32);
+    rqs_rows_kernel<KMAX><<<grid, kRowsThreads, smem, st>>>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy,
+                                                            lad_accum, n_rows, rpg, flags);
+    return check_launch("rqs_rows_kernel");
+}
+
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" int nfk_rqs_elementwise(const NfkSplineDesc* desc, int inverse, const float* x, const float* uw,
+                                   const float* uh, const float* ud, int64_t stride_w, int64_t stride_h,
+                                   int64_t stride_d, int64_t param_period, float* y, float* lad, int64_t n_elem,
+                                   int32_t* flags, void* stream) {
+    SplineParams p;
+    int rc = make_spline_params(desc, &p);
+    if (rc) return rc;
+    NFK_REQUIRE(n_elem >= 0, "n_elem < 0");
+    if (n_elem == 0) return NFK_OK;
+    NFK_REQUIRE(x && uw && uh && ud && y && lad, "NULL tensor pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = 256;
+    const int grid = (int)std::min<int64_t>((n_elem + threads - 1) / threads, 148 * 64);
+#define NFK_LAUNCH_EW(KM)                                                                                             \
+    rqs_elementwise_kernel<KM><<<grid, threads, 0, st>>>(p, inverse, x, uw, uh, ud, stride_w, stride_h, stride_d,      \
+                                                         param_period, y, lad, n_elem, flags)
+    if (p.num_bins <= 8) NFK_LAUNCH_EW(8);
+    else if (p.num_bins <= 16) NFK_LAUNCH_EW(16);
+    else if (p.num_bins <= 32) NFK_LAUNCH_EW(32);
+    else NFK_LAUNCH_EW(64);
+#undef NFK_LAUNCH_EW
+    return check_launch("rqs_elementwise_kernel");
+}
+
+extern "C" int nfk_rqs_rows(const NfkSplineDesc* desc, int inverse, const float* x, int64_t ldx, const float* params,
+                            const int32_t* t_cols, int32_t d_t, const int32_t* id_cols, int32_t d_id, float* y,
+                            int64_t ldy, float* lad_accum, int64_t n_rows, int32_t* flags, void* stream) {
+    SplineParams p;
+    int rc = make_spline_params(desc, &p);
+    if (rc) return rc;
+    NFK_REQUIRE(n_rows >= 0 && d_t >= 1 && d_id >= 0, "bad sizes n_rows=%lld d_t=%d d_id=%d", (long long)n_rows, d_t, d_id);
+    if (n_rows == 0) return NFK_OK;
+    NFK_REQUIRE(x && params && y, "NULL tensor pointer");
+    NFK_REQUIRE(d_id == 0 || id_cols, "id_cols is NULL");
+    NFK_REQUIRE(x != y, "y must not alias x");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.num_bins <= 8)
+        return launch_rows<8>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
+    if (p.num_bins <= 16)
+        return launch_rows<16>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
+    if (p.num_bins <= 32)
+        return launch_rows<32>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
+    return launch_rows<64>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
+}

@@ -1,0 +1,153 @@
+"""Tensor-level wrappers over the C ABI (include/nfk.h).  Each function enqueues exactly the kernels the
+C entry point launches on the current CUDA stream; tensors are only used for their storage."""
+import ctypes
+
+import torch
+
+from . import _native as N
+
+
+#: bench.py sets this to a list to collect (tag, rows, start_event, end_event) around tagged launches
+TIMELINE = None
+
+
+class timed:
+    """Brackets a launch with CUDA events on the current stream when bench.py asked for a timeline."""
+
+    def __init__(self, tag, rows):
+        self.tag, self.rows = tag, rows
+
+    def __enter__(self):
+        if TIMELINE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if TIMELINE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMELINE.append((self.tag, self.rows, self.e0, e1))
+
+
+def _rows2d(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+        raise ValueError("{} must be a 2-D float32 CUDA tensor with unit column stride".format(name))
+    return t
+
+
+def native_ok(t):
+    """True when `t` is something the native path takes: CUDA, fp32, no autograd graph to build."""
+    return t.is_cuda and t.dtype == torch.float32 and not (torch.is_grad_enabled() and t.requires_grad)
+
+
+def new_flags(device):
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def index_tensor(idx, device):
+    return idx.to(device=device, dtype=torch.int32).contiguous()
+
+
+def fill_(t, value):
+    N.check(N.lib().nfk_fill(t.data_ptr(), float(value), t.numel(), N.stream()))
+    return t
+
+
+def add_const_(lad, c):
+    N.check(N.lib().nfk_add_const(lad.data_ptr(), float(c), lad.numel(), N.stream()))
+    return lad
+
+
+def zeros_lad(x):
+    return fill_(torch.empty(x.shape[0], dtype=torch.float32, device=x.device), 0.0)
+
+
+def linear(x, weight, bias=None, residual=None, relu_in=False, relu_out=False, out=None):
+    """out = post(pre(x) @ weight.T + bias) + residual; weight is [out_features, in_features] (nn.Linear layout)."""
+    _rows2d(x, "x")
+    _rows2d(weight, "weight")
+    n, k = x.shape
+    o = weight.shape[0]
+    if weight.shape[1] != k:
+        raise ValueError("weight is {}x{}, x has {} features".format(o, weight.shape[1], k))
+    if out is None:
+        out = torch.empty(n, o, dtype=torch.float32, device=x.device)
+    _rows2d(out, "out")
+    if bias is not None and not bias.is_contiguous():
+        bias = bias.contiguous()
+    N.check(N.lib().nfk_linear(x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0), N.ptr(bias),
+                               N.ptr(residual), residual.stride(0) if residual is not None else 0, out.data_ptr(),
+                               out.stride(0), n, k, o, int(relu_in), int(relu_out), N.stream()))
+    return out
+
+
+def gather_cols(x, cols_i32, out=None):
+    _rows2d(x, "x")
+    n = x.shape[0]
+    c = cols_i32.numel()
+    if out is None:
+        out = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    N.check(N.lib().nfk_gather_cols(x.data_ptr(), x.stride(0), cols_i32.data_ptr(), c, out.data_ptr(), out.stride(0), n,
+                                    N.stream()))
+    return out
+
+
+def actnorm(x, scale, shift, lad_accum, lad_const, inverse):
+    _rows2d(x, "x")
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    N.check(N.lib().nfk_actnorm(x.data_ptr(), x.stride(0), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), y.stride(0),
+                                N.ptr(lad_accum), float(lad_const), x.shape[0], x.shape[1], int(inverse), N.stream()))
+    return y
+
+
+def rqs_rows(desc, inverse, x, params, t_cols, id_cols, lad_accum, flags, out=None):
+    _rows2d(x, "x")
+    _rows2d(params, "params")
+    if not params.is_contiguous():
+        raise ValueError("params must be contiguous")
+    y = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    N.check(N.lib().nfk_rqs_rows(ctypes.byref(desc), int(inverse), x.data_ptr(), x.stride(0), params.data_ptr(),
+                                 N.ptr(t_cols), t_cols.numel(), N.ptr(id_cols), id_cols.numel(), y.data_ptr(), y.stride(0),
+                                 N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
+    return y
+
+
+def rqs_elementwise(desc, inverse, x, uw, uh, ud, param_period=0, flags=None):
+    """x: any shape (contiguous); uw/uh/ud: [..., K], [..., K], [..., K-1|K+1] contiguous on the last dim."""
+    x = x.contiguous()
+    uw, uh, ud = uw.contiguous(), uh.contiguous(), ud.contiguous()
+    y = torch.empty_like(x)
+    lad = torch.empty_like(x)
+    N.check(N.lib().nfk_rqs_elementwise(ctypes.byref(desc), int(inverse), x.data_ptr(), uw.data_ptr(), uh.data_ptr(),
+                                        ud.data_ptr(), uw.shape[-1], uh.shape[-1], ud.shape[-1], int(param_period),
+                                        y.data_ptr(), lad.data_ptr(), x.numel(), N.ptr(flags), N.stream()))
+    return y, lad
+
+
+def affine_coupling_rows(x, params, mult, scale_activation, inverse, t_cols, id_cols, lad_accum, out=None):
+    _rows2d(x, "x")
+    if not params.is_contiguous():
+        raise ValueError("params must be contiguous")
+    y = torch.empty_like(x, memory_format=torch.contiguous_format) if out is None else out
+    N.check(N.lib().nfk_affine_coupling_rows(x.data_ptr(), x.stride(0), params.data_ptr(), int(mult), int(scale_activation),
+                                             int(inverse), N.ptr(t_cols), t_cols.numel(), N.ptr(id_cols), id_cols.numel(),
+                                             y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.stream()))
+    return y
+
+
+def std_normal_log_prob(z, log_z, lad=None):
+    _rows2d(z, "z")
+    out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+    N.check(N.lib().nfk_std_normal_log_prob(z.data_ptr(), z.stride(0), z.shape[1], float(log_z), N.ptr(lad), out.data_ptr(),
+                                            z.shape[0], N.stream()))
+    return out
+
+
+def raise_for_flags(flags):
+    """Mirror the reference's exceptions (rational_quadratic.py:81-82, :142).  One device->host read."""
+    from .transforms.base import InputOutsideDomain
+    v = int(flags.item())
+    if v & 1:
+        raise InputOutsideDomain()
+    if v & 2:
+        raise AssertionError("rational-quadratic spline inverse: negative discriminant")

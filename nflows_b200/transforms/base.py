@@ -1,0 +1,219 @@
+"""Transform protocol, composition and the native execution chain.
+
+Public contract = reference nflows/transforms/base.py:10-60, 215-231: a Transform maps
+``(inputs, context) -> (outputs, logabsdet[B])`` and has an ``inverse`` with the same signature.
+
+B200-native addition: transforms that own CUDA kernels implement ``_native_apply(x, lad, flags, inverse)``
+which enqueues kernels on the current stream, read-modify-writes the running ``lad`` buffer (so
+``CompositeTransform`` never materialises per-transform log-dets, unlike ``_cascade`` at base.py:44-52) and
+returns the output tensor.  Inputs that are not (CUDA, fp32, 2-D, no autograd) take the differentiable
+torch path ``_eager`` -- that is the device-agnostic/training path of the API, never a substitute for the
+kernels on CUDA inference."""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import config
+from .. import kernels as K
+from ..utils import typechecks as check
+
+
+class InverseNotAvailable(Exception):
+    """Raised by transforms that have no inverse."""
+
+
+class InputOutsideDomain(Exception):
+    """Raised when an input is outside the domain of a transform (e.g. a constrained spline)."""
+
+
+def params_frozen(module):
+    """True when running `module` cannot need a backward pass."""
+    return not torch.is_grad_enabled() or not any(p.requires_grad for p in module.parameters())
+
+
+class Transform(nn.Module):
+    """Base class of all transforms."""
+
+    def forward(self, inputs, context=None):
+        return self._run(inputs, context, inverse=False)
+
+    def inverse(self, inputs, context=None):
+        return self._run(inputs, context, inverse=True)
+
+    # -- subclass hooks ---------------------------------------------------------------------------------
+    def _eager(self, inputs, context, inverse):
+        if inverse:
+            raise InverseNotAvailable()
+        raise NotImplementedError()
+
+    def _native_ready(self, inputs, context):
+        return False
+
+    def _native_apply(self, inputs, lad, flags, inverse, context=None):
+        raise NotImplementedError()
+
+    # -- dispatch ---------------------------------------------------------------------------------------
+    def _run(self, inputs, context, inverse):
+        if torch.is_tensor(inputs) and self._native_ready(inputs, context):
+            x = inputs if inputs.stride(-1) == 1 else inputs.contiguous()
+            lad = K.zeros_lad(x)
+            flags = K.new_flags(x.device)
+            out = self._native_apply(x, lad, flags, inverse, context)
+            if config.check_domain:
+                K.raise_for_flags(flags)
+            return out, lad
+        return self._eager(inputs, context, inverse)
+
+
+def _flatten(transform, inverse, out):
+    """Leaves of nested CompositeTransforms / InverseTransforms in execution order, as (leaf, inverse)."""
+    if isinstance(transform, CompositeTransform):
+        children = list(transform._transforms)
+        for child in (reversed(children) if inverse else children):
+            _flatten(child, inverse, out)
+    elif isinstance(transform, InverseTransform):
+        _flatten(transform._transform, not inverse, out)
+    else:
+        out.append((transform, inverse))
+    return out
+
+
+class CompositeTransform(Transform):
+    """Applies transforms in the order given (reference base.py:32-60)."""
+
+    def __init__(self, transforms):
+        super().__init__()
+        self._transforms = nn.ModuleList(transforms)
+        self._affine_cache = {}
+
+    def _eager(self, inputs, context, inverse):
+        children = list(self._transforms)
+        outputs = inputs
+        total = inputs.new_zeros(inputs.shape[0])
+        for t in (reversed(children) if inverse else children):
+            outputs, lad = t.inverse(outputs, context) if inverse else t(outputs, context)
+            total += lad
+        return outputs, total
+
+    def _native_ready(self, inputs, context):
+        return K.native_ok(inputs) and inputs.dim() == 2 and params_frozen(self)
+
+    def _native_apply(self, inputs, lad, flags, inverse, context=None):
+        from .fused_affine import AffineRun, is_affine_leaf
+
+        leaves = _flatten(self, inverse, [])
+        x = inputs
+        i = 0
+        while i < len(leaves):
+            leaf, inv = leaves[i]
+            # fold a run of per-feature affine / permutation / LU transforms into ONE dense layer
+            j = i
+            has_lu = False
+            while j < len(leaves) and is_affine_leaf(leaves[j][0], x):
+                has_lu = has_lu or leaves[j][0].__class__.__name__ in ("LULinear",)
+                j += 1
+            if has_lu and j - i >= 1:
+                run = AffineRun.cached(self._affine_cache, leaves[i:j], x.device)
+                x = run.apply(x, lad)
+                i = j
+                continue
+            if leaf._native_ready(x, context):
+                x = leaf._native_apply(x, lad, flags, inv, context)
+            else:
+                x, l = leaf.inverse(x, context) if inv else leaf(x, context)
+                lad += l
+                if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+                    raise RuntimeError("{} changed the tensor layout inside a native chain".format(type(leaf).__name__))
+                x = x.contiguous()
+            i += 1
+        return x
+
+
+class InverseTransform(Transform):
+    """Swaps forward and inverse of a transform (reference base.py:215-231)."""
+
+    def __init__(self, transform):
+        super().__init__()
+        self._transform = transform
+
+    def forward(self, inputs, context=None):
+        return self._transform.inverse(inputs, context)
+
+    def inverse(self, inputs, context=None):
+        return self._transform(inputs, context)
+
+
+class MultiscaleCompositeTransform(Transform):
+    """Multiscale architecture of RealNVP (reference base.py:63-212): after every transform but the last,
+    half of the current tensor (along ``split_dim``) is emitted and the other half carried on.  Forward
+    returns the flat concatenation of everything emitted.  Executed with torch views around the child
+    transforms (which run natively where they can)."""
+
+    def __init__(self, num_transforms, split_dim=1):
+        if not check.is_positive_int(num_transforms):
+            raise TypeError("Number of transforms must be a positive integer.")
+        if not check.is_positive_int(split_dim):
+            raise TypeError("Split dimension must be a positive integer.")
+        super().__init__()
+        self._transforms = nn.ModuleList()
+        self._output_shapes = []
+        self._num_transforms = num_transforms
+        self._split_dim = split_dim
+
+    def add_transform(self, transform, transform_output_shape):
+        """Registers the next transform; returns the shape its carried-on half will have, or None for the last."""
+        assert len(self._transforms) <= self._num_transforms
+        if len(self._transforms) == self._num_transforms:
+            raise RuntimeError("Adding more than {} transforms is not allowed.".format(self._num_transforms))
+        if (self._split_dim - 1) >= len(transform_output_shape):
+            raise ValueError("No split_dim in output shape")
+        if transform_output_shape[self._split_dim - 1] < 2:
+            raise ValueError("Size of dimension {} must be at least 2.".format(self._split_dim))
+        self._transforms.append(transform)
+        if len(self._transforms) == self._num_transforms:
+            self._output_shapes.append(tuple(transform_output_shape))
+            return None
+        shape = list(transform_output_shape)
+        emitted = list(shape)
+        emitted[self._split_dim - 1] = (shape[self._split_dim - 1] + 1) // 2
+        carried = list(shape)
+        carried[self._split_dim - 1] = shape[self._split_dim - 1] // 2
+        self._output_shapes.append(tuple(emitted))
+        return tuple(carried)
+
+    def forward(self, inputs, context=None):
+        if self._split_dim >= inputs.dim():
+            raise ValueError("No split_dim in inputs.")
+        if self._num_transforms != len(self._transforms):
+            raise RuntimeError("Expecting exactly {} transform(s) to be added.".format(self._num_transforms))
+        batch = inputs.shape[0]
+        total = inputs.new_zeros(batch)
+        pieces = []
+        carried = inputs
+        for k, t in enumerate(self._transforms):
+            out, lad = t(carried, context)
+            total += lad
+            if k < self._num_transforms - 1:
+                emitted, carried = torch.chunk(out, chunks=2, dim=self._split_dim)
+                assert emitted.shape[1:] == self._output_shapes[k]
+            else:
+                emitted = out
+            pieces.append(emitted.reshape(batch, -1))
+        return torch.cat(pieces, dim=-1), total
+
+    def inverse(self, inputs, context=None):
+        if inputs.dim() != 2:
+            raise ValueError("Expecting NxD inputs")
+        if self._num_transforms != len(self._transforms):
+            raise RuntimeError("Expecting exactly {} transform(s) to be added.".format(self._num_transforms))
+        batch = inputs.shape[0]
+        sizes = [int(np.prod(s)) for s in self._output_shapes]
+        chunks = torch.split(inputs, sizes, dim=1)
+        pieces = [c.reshape(batch, *s) for c, s in zip(chunks, self._output_shapes)]
+        total = inputs.new_zeros(batch)
+        carried, lad = self._transforms[-1].inverse(pieces[-1], context)
+        total += lad
+        for t, piece in zip(reversed(list(self._transforms)[:-1]), reversed(pieces[:-1])):
+            carried, lad = t.inverse(torch.cat([piece, carried], dim=self._split_dim), context)
+            total += lad
+        return carried, total

@@ -1,0 +1,101 @@
+"""Folding of consecutive ActNorm / Permutation / LULinear transforms into ONE dense layer.
+
+Each of these is an affine map of the feature vector (normalization.py:171-204, permutations.py:27-45,
+lu.py:56-91), so a run of them is y = A x + c with a batch-constant log|det|.  A and c are composed on the
+host in float64 from the transforms' parameters (tiny: D x D) and rounded once to fp32; the run then costs a
+single `nfk_linear` launch instead of one elementwise pass + one gather pass + two GEMMs, and the operand
+rounding is no worse than the reference's chain of fp32 ops.  Folded weights are cached per composite and
+rebuilt when any parameter changes (tensor version counters)."""
+import numpy as np
+import torch
+
+from .. import kernels as K
+
+
+def is_affine_leaf(leaf, x):
+    from .lu import LULinear
+    from .normalization import ActNorm
+    from .permutations import Permutation
+
+    if isinstance(leaf, ActNorm):
+        return x.dim() == 2 and not (leaf.training and not bool(leaf.initialized))
+    if isinstance(leaf, Permutation):
+        return leaf._dim == 1
+    return isinstance(leaf, LULinear)
+
+
+def _signature(leaves):
+    sig = []
+    for leaf, inv in leaves:
+        sig.append((id(leaf), inv, tuple((p.data_ptr(), p._version) for p in leaf.parameters()),
+                    tuple((b.data_ptr(), b._version) for b in leaf.buffers())))
+    return tuple(sig)
+
+
+class AffineRun:
+    def __init__(self, leaves, device):
+        from .lu import LULinear
+        from .normalization import ActNorm
+
+        d = None
+        for leaf, _ in leaves:
+            d = getattr(leaf, "features", None) or d
+            if isinstance(leaf, ActNorm):
+                d = leaf.log_scale.numel()
+        if d is None:
+            d = leaves[0][0]._permutation.numel()
+        A = np.eye(d, dtype=np.float64)
+        c = np.zeros(d, dtype=np.float64)
+        lad = 0.0
+        for leaf, inv in leaves:
+            if isinstance(leaf, ActNorm):
+                log_s = leaf.log_scale.detach().double().cpu().numpy()
+                t = leaf.shift.detach().double().cpu().numpy()
+                s = np.exp(log_s)
+                if inv:
+                    A = A / s[:, None]
+                    c = (c - t) / s
+                    lad -= log_s.sum()
+                else:
+                    A = A * s[:, None]
+                    c = s * c + t
+                    lad += log_s.sum()
+            elif isinstance(leaf, LULinear):
+                lower, upper, diag = leaf._dense_factors_f64()
+                b = leaf.bias.detach().double().cpu().numpy()
+                if inv:
+                    import scipy.linalg as sl
+                    rhs = np.concatenate([A, (c - b)[:, None]], axis=1)
+                    rhs = sl.solve_triangular(lower, rhs, lower=True, unit_diagonal=True)
+                    rhs = sl.solve_triangular(upper, rhs, lower=False)
+                    A, c = rhs[:, :-1], rhs[:, -1]
+                    lad -= np.log(diag).sum()
+                else:
+                    A = lower @ (upper @ A)
+                    c = lower @ (upper @ c) + b
+                    lad += np.log(diag).sum()
+            else:  # Permutation
+                perm = leaf._permutation.detach().cpu().numpy()
+                if inv:
+                    perm = np.argsort(perm, kind="stable")
+                A = A[perm, :]
+                c = c[perm]
+        self.weight = torch.from_numpy(np.ascontiguousarray(A)).float().to(device)
+        self.bias = torch.from_numpy(np.ascontiguousarray(c)).float().to(device)
+        self.lad_const = float(lad)
+
+    @classmethod
+    def cached(cls, cache, leaves, device):
+        sig = (_signature(leaves), str(device))
+        key = tuple((id(leaf), inv) for leaf, inv in leaves)
+        hit = cache.get(key)
+        if hit is None or hit[0] != sig:
+            hit = (sig, cls(leaves, device))
+            cache[key] = hit
+        return hit[1]
+
+    def apply(self, x, lad):
+        y = K.linear(x, self.weight, self.bias)
+        if self.lad_const != 0.0:
+            K.add_const_(lad, self.lad_const)
+        return y

@@ -1,0 +1,120 @@
+"""The public classes, run on CPU (device-agnostic torch path), against the reference's golden outputs.
+Checks constructor kwargs, state_dict key compatibility (load_state_dict of the REFERENCE's state_dict) and the
+host-side composition logic.  The CUDA kernels are checked in test_native_parity.py (-m gpu)."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from nflows_b200 import transforms as T
+from nflows_b200.distributions import StandardNormal
+from nflows_b200.flows import Flow
+from nflows_b200.flows import recipes
+from nflows_b200.nn.nets import ResidualNet
+from nflows_b200.utils import torchutils
+
+TOL = 2e-6
+
+
+@torch.no_grad()
+def test_cfg1_affine_flow_cpu():
+    g = load_golden("cfg1_affine")
+    flow = recipes.affine_flow_2d().eval()
+    flow.load_state_dict(g["sd"])            # strict: same keys as the reference
+    assert rel_err(flow.log_prob(g["x"]), g["log_prob"]) <= TOL
+    z, lad = flow._transform(g["x"])
+    assert rel_err(z, g["z"]) <= TOL and rel_err(lad, g["lad"]) <= TOL
+    xr, ladr = flow._transform.inverse(g["z"])
+    assert rel_err(xr, g["x_roundtrip"]) <= TOL and rel_err(ladr, g["lad_inverse"]) <= TOL
+    assert flow.sample(5).shape == (5, 2)
+    s, lp = flow.sample_and_log_prob(7)
+    assert rel_err(lp, flow.log_prob(s)) <= 1e-5
+
+
+@torch.no_grad()
+def test_affine_variants_cpu():
+    g = load_golden("affine_variants")
+    f = lambda i, o: ResidualNet(i, o, hidden_features=16)
+    mask = torchutils.create_mid_split_binary_mask(10)
+    tg = T.AffineCouplingTransform(mask, f, scale_activation=T.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION).eval()
+    tg.load_state_dict(g["sd_general"])
+    y, l = tg(g["x"])
+    assert rel_err(y, g["y_general"]) <= TOL and rel_err(l, g["lad_general"]) <= TOL
+    ta = T.AdditiveCouplingTransform(mask, f).eval()
+    ta.load_state_dict(g["sd_additive"])
+    y, l = ta(g["x"])
+    assert rel_err(y, g["y_additive"]) <= TOL and torch.equal(l, torch.zeros_like(l))
+
+
+@torch.no_grad()
+def test_cfg2_rq_coupling_cpu():
+    g = load_golden("cfg2_rq_coupling")
+    t = recipes.rq_coupling_layer().eval()
+    t.load_state_dict(g["sd"])
+    y, l = t(g["x"])
+    assert rel_err(y, g["y"]) <= TOL and rel_err(l, g["lad"]) <= 1e-5
+    assert torch.equal(y[:, t.identity_features], g["x"][:, t.identity_features])
+    xi, li = t.inverse(g["x"])
+    assert rel_err(xi, g["xinv"]) <= TOL and rel_err(li, g["ladinv"]) <= 1e-5
+
+
+@torch.no_grad()
+def test_rq_constrained_cpu():
+    g = load_golden("rq_coupling_constrained")
+    t = T.PiecewiseRationalQuadraticCouplingTransform(
+        mask=torchutils.create_mid_split_binary_mask(11),
+        transform_net_create_fn=lambda i, o: ResidualNet(i, o, hidden_features=24, num_blocks=1),
+        num_bins=5, tails=None, min_bin_width=2e-3, min_bin_height=3e-3, min_derivative=4e-3).eval()
+    t.load_state_dict(g["sd"])
+    y, l = t(g["x"])
+    assert rel_err(y, g["y"]) <= TOL and rel_err(l, g["lad"]) <= 1e-5
+    with pytest.raises(T.InputOutsideDomain):
+        t(g["x"] + 1.0)
+
+
+@torch.no_grad()
+def test_linear_transforms_cpu():
+    g = load_golden("linear_transforms")
+    d = g["x"].shape[1]
+    an, lu, pm = T.ActNorm(d).eval(), T.LULinear(d, identity_init=False).eval(), T.RandomPermutation(d).eval()
+    an.load_state_dict(g["sd_actnorm"]); lu.load_state_dict(g["sd_lu"]); pm.load_state_dict(g["sd_perm"])
+    for name, m in (("actnorm", an), ("lu", lu), ("perm", pm)):
+        y, l = m(g["x"])
+        assert rel_err(y, g[name + "_y"]) <= TOL and rel_err(l, g[name + "_lad"]) <= TOL
+        y, l = m.inverse(g["x"])
+        assert rel_err(y, g[name + "_xinv"]) <= 1e-5 and rel_err(l, g[name + "_ladinv"]) <= TOL
+    assert torch.equal(pm(g["x"])[0], g["x"][:, g["sd_perm"]["_permutation"]])
+    assert rel_err(lu.weight(), g["lu_weight"]) <= TOL
+    assert rel_err(lu.weight_inverse(), g["lu_weight_inverse"]) <= 1e-5
+    # cache protocol (reference linear.py:46-96)
+    lu.use_cache(True)
+    y1, _ = lu(g["x"])
+    assert lu.cache.weight is not None and rel_err(y1, g["lu_y"]) <= 1e-5
+    lu.train()
+    assert lu.cache.weight is None
+
+
+@torch.no_grad()
+def test_nsf_small_cpu():
+    g = load_golden("nsf_small")
+    flow = recipes.rq_nsf(g["features"], g["hidden"], g["layers"]).eval()
+    flow.load_state_dict(g["sd"])
+    assert rel_err(flow.log_prob(g["x"]), g["log_prob"]) <= TOL
+    xs, lads = flow._transform.inverse(g["noise"])
+    assert rel_err(xs, g["sample"]) <= 1e-5 and rel_err(lads, g["lad_inverse"]) <= 1e-5
+    assert rel_err(flow.transform_to_noise(g["x"]), g["z"]) <= TOL
+
+
+@torch.no_grad()
+def test_seeded_construction_matches_reference_weights():
+    """Constructors consume the RNG like the reference's: the seed-only fixtures depend on it."""
+    g = load_golden("cfg2_rq_coupling")
+    torch.manual_seed(0)
+    t = recipes.rq_coupling_layer()
+    for k, v in g["sd"].items():
+        assert torch.equal(t.state_dict()[k], v), k
+    g = load_golden("nsf784_layer")
+    torch.manual_seed(g["seed"])
+    flow = recipes.perturb_(recipes.rq_nsf(g["features"], g["hidden"], g["layers"]).eval(), g["perturb_seed"])
+    ck = float(sum(v.double().abs().sum() for v in flow.state_dict().values() if v.is_floating_point()))
+    assert abs(ck - g["checksum"]) <= 1e-9 * abs(g["checksum"])
+    assert rel_err(flow.log_prob(g["x"]), g["log_prob"]) <= TOL

@@ -1,0 +1,334 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden outputs and with the CPU oracle.
+
+Tolerance: 1e-5 relative (`rel_err`: max |a-b| / max(|a|,|b|,1)), the bar BASELINE.json states for fp32;
+identity columns and permutations must be bit-exact.  Per-layer log|det| of a spline layer additionally gets
+the fp64 sandwich of SURVEY.md section 8c where the reference's own fp32 round-off exceeds 1e-5."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from nflows_b200 import _native
+from nflows_b200 import config
+from nflows_b200 import kernels as K
+from nflows_b200 import transforms as T
+from nflows_b200.flows import recipes
+from nflows_b200.nn.nets import MLP, ResidualNet
+from nflows_b200.transforms.splines import rational_quadratic as rq
+from nflows_b200.utils import torchutils
+from oracle import flow_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+class native_launches:
+    """Asserts that the block launched our kernels (no silent torch fallback)."""
+
+    def __enter__(self):
+        self.before = _native.launch_count()
+        return self
+
+    def __exit__(self, *exc):
+        if exc[0] is None:
+            assert _native.launch_count() > self.before, "no native kernel was launched"
+
+
+def to_dev(module, dev):
+    return module.eval().to(dev)
+
+
+@torch.no_grad()
+def test_searchsorted_and_identity_spline(cuda_device):
+    # identity-init known answer (reference tests/transforms/splines/rational_quadratic_test.py:33-62, 116-146)
+    shape, k = (2, 3, 4), 10
+    zeros = torch.zeros(*shape, k, device=cuda_device)
+    x = torch.rand(*shape, device=cuda_device)
+    with native_launches():
+        y, lad = rq.rational_quadratic_spline(x, zeros, zeros, torch.zeros(*shape, k + 1, device=cuda_device),
+                                              enable_identity_init=True)
+    assert rel_err(y.cpu(), x.cpu()) <= 1e-6 and float(lad.abs().max()) <= 1e-6
+    xt = (torch.rand(*shape, device=cuda_device) - 0.5) * 4
+    y, lad = rq.unconstrained_rational_quadratic_spline(xt, zeros, zeros, torch.zeros(*shape, k - 1, device=cuda_device),
+                                                        enable_identity_init=True)
+    assert rel_err(y.cpu(), xt.cpu()) <= 1e-6 and float(lad.abs().max()) <= 1e-6
+
+
+@torch.no_grad()
+def test_spline_function_vectors(cuda_device):
+    g = load_golden("spline")
+    dev = lambda k: g[k].to(cuda_device)
+    for inv in (False, True):
+        with native_launches():
+            y, l = rq.unconstrained_rational_quadratic_spline(dev("x_tails"), dev("uw"), dev("uh"), dev("ud_tails"), inverse=inv,
+                                                              tails="linear", tail_bound=g["tail_bound"])
+        wy, wl = g["tails_inv%d" % inv]
+        assert rel_err(y.cpu(), wy) <= TOL and rel_err(l.cpu(), wl) <= TOL
+        # exact edge semantics: x=-B -> (-B, 0); outside -> identity, lad 0; NaN -> NaN, lad 0
+        assert float(y[0]) == -3.0 and float(l[0]) == 0.0
+        assert float(y[2]) == float(g["x_tails"][2]) and float(l[2]) == 0.0
+        assert torch.isnan(y[6]) and float(l[6]) == 0.0 and float(y[7]) == 1e30
+        y, l = rq.rational_quadratic_spline(dev("x_constrained"), dev("uw"), dev("uh"), dev("ud_constrained"), inverse=inv)
+        wy, wl = g["constrained_inv%d" % inv]
+        assert rel_err(y.cpu(), wy) <= TOL and rel_err(l.cpu(), wl) <= TOL
+        y, l = rq.rational_quadratic_spline(dev("x_constrained") * 4 - 1, dev("uw"), dev("uh"), dev("ud_constrained"),
+                                            inverse=inv, left=-1.0, right=3.0, bottom=-1.0, top=3.0, min_bin_width=1e-2,
+                                            min_bin_height=2e-2, min_derivative=5e-2)
+        wy, wl = g["constrained_box_inv%d" % inv]
+        assert rel_err(y.cpu(), wy) <= TOL and rel_err(l.cpu(), wl) <= TOL
+
+
+@torch.no_grad()
+def test_spline_error_conventions(cuda_device):
+    k = 4
+    z = torch.zeros(5, k, device=cuda_device)
+    d = torch.zeros(5, k + 1, device=cuda_device)
+    x = torch.tensor([0.1, 0.5, 1.5, 0.2, 0.3], device=cuda_device)
+    with pytest.raises(T.InputOutsideDomain):
+        rq.rational_quadratic_spline(x, z, z, d)
+    with pytest.raises(ValueError):
+        rq.rational_quadratic_spline(x.clamp(0, 1), z, z, d, min_bin_width=0.3)
+    with pytest.raises(RuntimeError):
+        rq.unconstrained_rational_quadratic_spline(x, z, z, d[:, :k - 1], tails="cubic")
+    # empty input is fine
+    e = torch.zeros(0, device=cuda_device)
+    y, l = rq.rational_quadratic_spline(e, z[:0], z[:0], d[:0])
+    assert y.shape == (0,) and l.shape == (0,)
+
+
+@torch.no_grad()
+def test_cfg1_affine_flow(cuda_device):
+    g = load_golden("cfg1_affine")
+    flow = recipes.affine_flow_2d()
+    flow.load_state_dict(g["sd"])
+    flow = to_dev(flow, cuda_device)
+    x = g["x"].to(cuda_device)
+    with native_launches():
+        lp = flow.log_prob(x)
+    assert rel_err(lp.cpu(), g["log_prob"]) <= TOL
+    z, lad = flow._transform(x)
+    assert rel_err(z.cpu(), g["z"]) <= TOL and rel_err(lad.cpu(), g["lad"]) <= TOL
+    xr, ladr = flow._transform.inverse(g["z"].to(cuda_device))
+    assert rel_err(xr.cpu(), g["x_roundtrip"]) <= TOL and rel_err(ladr.cpu(), g["lad_inverse"]) <= TOL
+    # identity halves are bit-exact (reference tests/transforms/coupling_test.py:50)
+    t0 = flow._transform._transforms[0]
+    y0, _ = t0(x)
+    assert torch.equal(y0[:, t0.identity_features], x[:, t0.identity_features])
+    assert flow.sample(5).shape == (5, 2)
+    s, lps = flow.sample_and_log_prob(64)
+    assert rel_err(lps.cpu(), flow.log_prob(s).cpu()) <= 1e-4
+
+
+@torch.no_grad()
+def test_affine_variants(cuda_device):
+    g = load_golden("affine_variants")
+    f = lambda i, o: ResidualNet(i, o, hidden_features=16)
+    mask = torchutils.create_mid_split_binary_mask(10)
+    tg = T.AffineCouplingTransform(mask, f, scale_activation=T.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION)
+    tg.load_state_dict(g["sd_general"])
+    tg = to_dev(tg, cuda_device)
+    x = g["x"].to(cuda_device)
+    with native_launches():
+        y, l = tg(x)
+    assert rel_err(y.cpu(), g["y_general"]) <= TOL and rel_err(l.cpu(), g["lad_general"]) <= TOL
+    y, l = tg.inverse(x)
+    assert rel_err(y.cpu(), g["xinv_general"]) <= TOL and rel_err(l.cpu(), g["ladinv_general"]) <= TOL
+    ta = T.AdditiveCouplingTransform(mask, f)
+    ta.load_state_dict(g["sd_additive"])
+    ta = to_dev(ta, cuda_device)
+    with native_launches():
+        y, l = ta(x)
+    assert rel_err(y.cpu(), g["y_additive"]) <= TOL and torch.equal(l.cpu(), torch.zeros(x.shape[0]))
+
+
+@torch.no_grad()
+def test_cfg2_rq_coupling(cuda_device):
+    g = load_golden("cfg2_rq_coupling")
+    t = recipes.rq_coupling_layer()
+    t.load_state_dict(g["sd"])
+    t = to_dev(t, cuda_device)
+    x = g["x"].to(cuda_device)
+    for suffix in ("", "_x3"):
+        if suffix:
+            for name, p in t.named_parameters():
+                if "final_layer" in name:
+                    p.mul_(3.0)
+        with native_launches():
+            y, l = t(x)
+        assert rel_err(y.cpu(), g["y" + suffix]) <= TOL and rel_err(l.cpu(), g["lad" + suffix]) <= 3e-5
+        assert torch.equal(y[:, t.identity_features], x[:, t.identity_features])
+        xi, li = t.inverse(x)
+        assert rel_err(xi.cpu(), g["xinv" + suffix]) <= (TOL if not suffix else 1e-4)
+        assert rel_err(li.cpu(), g["ladinv" + suffix]) <= (3e-5 if not suffix else 1e-3)
+        back, lb = t.inverse(y)
+        assert rel_err(back.cpu(), g["x"]) <= 1e-4
+
+
+@torch.no_grad()
+def test_rq_coupling_constrained_and_domain_error(cuda_device):
+    g = load_golden("rq_coupling_constrained")
+    t = T.PiecewiseRationalQuadraticCouplingTransform(
+        mask=torchutils.create_mid_split_binary_mask(11),
+        transform_net_create_fn=lambda i, o: ResidualNet(i, o, hidden_features=24, num_blocks=1),
+        num_bins=5, tails=None, min_bin_width=2e-3, min_bin_height=3e-3, min_derivative=4e-3)
+    t.load_state_dict(g["sd"])
+    t = to_dev(t, cuda_device)
+    x = g["x"].to(cuda_device)
+    with native_launches():
+        y, l = t(x)
+    assert rel_err(y.cpu(), g["y"]) <= TOL and rel_err(l.cpu(), g["lad"]) <= 3e-5
+    xi, li = t.inverse(x)
+    assert rel_err(xi.cpu(), g["xinv"]) <= 1e-4 and rel_err(li.cpu(), g["ladinv"]) <= 1e-3
+    with pytest.raises(T.InputOutsideDomain):
+        t(x + 1.0)
+    with pytest.raises(ValueError):
+        t(x[:, :5])
+
+
+@torch.no_grad()
+def test_unrecognised_conditioner_uses_spline_epilogue_kernel(cuda_device):
+    """A conditioner that is not a relu ResidualNet/MLP runs in torch; the spline epilogue is still ours."""
+
+    class Odd(torch.nn.Module):
+        def __init__(self, i, o):
+            super().__init__()
+            self.hidden_features = 16
+            self.a, self.b = torch.nn.Linear(i, 16), torch.nn.Linear(16, o)
+
+        def forward(self, x, context=None):
+            return self.b(torch.tanh(self.a(x)))
+
+    torch.manual_seed(0)
+    t = T.PiecewiseRationalQuadraticCouplingTransform(torchutils.create_alternating_binary_mask(9), Odd, num_bins=6,
+                                                      tails="linear", tail_bound=2.0).eval()
+    x = torch.randn(333, 9)
+    sd = {k: v.clone() for k, v in t.state_dict().items()}
+    idf, trf = sd["identity_features"], sd["transform_features"]
+    params = t.transform_net(x[:, idf]).reshape(333, len(trf), -1)
+    yt, lad = O.rq_spline_unconstrained(x[:, trf], params[..., :6] / 4.0, params[..., 6:12] / 4.0, params[..., 12:].clone(),
+                                        tail_bound=2.0)
+    t = t.to(cuda_device)
+    with native_launches():
+        y, l = t(x.to(cuda_device))
+    assert rel_err(y[:, trf.to(cuda_device)].cpu(), yt) <= TOL and rel_err(l.cpu(), lad.sum(1)) <= 3e-5
+    # MLP conditioner goes through the dense chain
+    t2 = T.PiecewiseRationalQuadraticCouplingTransform(
+        torchutils.create_alternating_binary_mask(9), lambda i, o: MLP([i], [o], [32, 32]), num_bins=6, tails="linear",
+        tail_bound=2.0).eval()
+    with pytest.warns(UserWarning):
+        y_cpu, l_cpu = t2(x)
+    t2 = t2.to(cuda_device)
+    with pytest.warns(UserWarning):
+        y2, l2 = t2(x.to(cuda_device))
+    assert rel_err(y2.cpu(), y_cpu) <= TOL and rel_err(l2.cpu(), l_cpu) <= 3e-5
+
+
+@torch.no_grad()
+def test_linear_transforms(cuda_device):
+    g = load_golden("linear_transforms")
+    d = g["x"].shape[1]
+    an, lu, pm = T.ActNorm(d), T.LULinear(d, identity_init=False), T.RandomPermutation(d)
+    an.load_state_dict(g["sd_actnorm"]); lu.load_state_dict(g["sd_lu"]); pm.load_state_dict(g["sd_perm"])
+    x = g["x"].to(cuda_device)
+    for name, m in (("actnorm", an), ("lu", lu), ("perm", pm)):
+        m = to_dev(m, cuda_device)
+        with native_launches():
+            y, l = m(x)
+        assert rel_err(y.cpu(), g[name + "_y"]) <= TOL and rel_err(l.cpu(), g[name + "_lad"]) <= TOL, name
+        y, l = m.inverse(x)
+        assert rel_err(y.cpu(), g[name + "_xinv"]) <= 1e-4 and rel_err(l.cpu(), g[name + "_ladinv"]) <= TOL, name
+    y, _ = pm(x)
+    assert torch.equal(y.cpu(), g["x"][:, g["sd_perm"]["_permutation"]])        # bit-exact indexing
+    y, _ = pm.inverse(y)
+    assert torch.equal(y, x)
+    # parameter update invalidates the folded-weight cache
+    lu.bias.add_(1.0)
+    y2, _ = lu(x)
+    assert rel_err(y2.cpu(), g["lu_y"] + 1.0) <= TOL
+
+
+@torch.no_grad()
+def test_nsf_small_flow_fused_and_unfused(cuda_device):
+    g = load_golden("nsf_small")
+    flow = recipes.rq_nsf(g["features"], g["hidden"], g["layers"])
+    flow.load_state_dict(g["sd"])
+    flow = to_dev(flow, cuda_device)
+    x = g["x"].to(cuda_device)
+    with native_launches():
+        lp = flow.log_prob(x)
+    assert rel_err(lp.cpu(), g["log_prob"]) <= TOL
+    z, lad = flow._transform(x)
+    assert rel_err(z.cpu(), g["z"]) <= 5e-5 and rel_err(lad.cpu(), g["lad"]) <= 3e-5
+    xs, lads = flow._transform.inverse(g["noise"].to(cuda_device))
+    assert rel_err(xs.cpu(), g["sample"]) <= 1e-4 and rel_err(lads.cpu(), g["lad_inverse"]) <= 1e-4
+    # transform-by-transform (no affine folding) agrees with the folded chain
+    out, total = x, torch.zeros(x.shape[0], device=cuda_device)
+    for t in flow._transform._transforms:
+        out, l = t(out)
+        total += l
+    assert rel_err(out, z) <= 2e-5 and rel_err(total, lad) <= 2e-5
+    # ragged / tiny batches
+    for n in (1, 3, 130):
+        assert rel_err(flow.log_prob(x[:n]).cpu(), g["log_prob"][:n]) <= TOL
+    assert flow.log_prob(x[:0]).shape == (0,)
+
+
+@torch.no_grad()
+def test_nsf784_layer_and_full_flow_seeded(cuda_device):
+    """Full-shape cfg-3 weights re-created from the seed (the fixture stores only inputs/outputs/checksum)."""
+    for name in ("nsf784_layer", "nsf784_full"):
+        g = load_golden(name)
+        torch.manual_seed(g["seed"])
+        flow = recipes.perturb_(recipes.rq_nsf(g["features"], g["hidden"], g["layers"]).eval(), g["perturb_seed"])
+        ck = float(sum(v.double().abs().sum() for v in flow.state_dict().values() if v.is_floating_point()))
+        if abs(ck - g["checksum"]) > 1e-9 * abs(g["checksum"]):
+            pytest.skip("torch CPU RNG stream differs from the fixture's")
+        flow = to_dev(flow, cuda_device)
+        x = g["x"].to(cuda_device)
+        with native_launches():
+            lp = flow.log_prob(x)
+        assert rel_err(lp.cpu(), g["log_prob"]) <= TOL, name
+        if name == "nsf784_layer":
+            z, lad = flow._transform(x)
+            assert rel_err(z.cpu(), g["z"]) <= TOL
+            # fp64 sandwich for the per-layer log|det| (the reference itself is ~3e-5 from fp64 here)
+            ref_gap = rel_err(g["lad"], g["lad_fp64"])
+            assert rel_err(lad.cpu(), g["lad_fp64"]) <= max(2 * ref_gap, TOL)
+            xi, li = flow._transform.inverse(x)
+            assert rel_err(xi.cpu(), g["xinv"]) <= 1e-4 and rel_err(li.cpu(), g["ladinv"]) <= 1e-4
+        else:
+            assert rel_err(lp.cpu(), g["log_prob_fp64"]) <= TOL
+
+
+@torch.no_grad()
+def test_oracle_parity_on_random_rows_of_a_large_batch(cuda_device):
+    """Rows are independent: run a large batch on the GPU, check a random subset against the CPU oracle."""
+    torch.manual_seed(0)
+    flow = recipes.perturb_(recipes.rq_nsf(features=96, hidden_features=64, num_layers=4).eval())
+    sd = {k: v.clone() for k, v in flow.state_dict().items()}
+    flow = flow.to(cuda_device)
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    x = torch.randn(1 << 17, 96, device=cuda_device, generator=gen) * 1.5
+    lp = flow.log_prob(x)
+    rows = torch.randint(0, x.shape[0], (2048,), generator=torch.Generator().manual_seed(6))
+    want = O.flow_log_prob(sd, O.nsf_spec(4), x[rows.to(cuda_device)].cpu())
+    assert rel_err(lp[rows.to(cuda_device)].cpu(), want) <= TOL
+    # chunk-consistency: a different batch split gives the same per-row numbers bit-for-bit
+    assert torch.equal(flow.log_prob(x[: 1 << 12]), lp[: 1 << 12])
+    # encode -> decode round trip at scale
+    z = flow.transform_to_noise(x[: 1 << 14])
+    back, _ = flow._transform.inverse(z)
+    assert rel_err(back, x[: 1 << 14]) <= 2e-3
+
+
+@torch.no_grad()
+def test_domain_check_can_be_disabled(cuda_device):
+    k = 4
+    z = torch.zeros(3, k, device=cuda_device)
+    d = torch.zeros(3, k + 1, device=cuda_device)
+    x = torch.tensor([0.1, 1.5, 0.3], device=cuda_device)
+    config.check_domain = False
+    try:
+        y, _ = rq.rational_quadratic_spline(x, z, z, d)
+        assert y.shape == (3,)
+    finally:
+        config.check_domain = True
