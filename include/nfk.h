@@ -86,6 +86,21 @@ int nfk_linear(const float* X, int64_t ldx, const float* W, int64_t ldw, const f
                int64_t ldr, float* Y, int64_t ldy, int64_t n_rows, int32_t in_features, int32_t out_features,
                int relu_in, int relu_out, void* stream);
 
+/* Tensor-core version of nfk_linear (tcgen05.mma kind::tf32, TMA-fed, accumulators in TMEM) with fp32-equivalent
+ * operand precision: every operand is a split pair v = v_hi + v_lo with v_hi = round-to-nearest TF32 of v (fp32
+ * container) and v_lo = v - v_hi, and each K-step accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.  The epilogue can
+ * emit the fp32 result Y and/or the split pair of Y (of relu(Y) when split_relu) that the next layer consumes.
+ * Requires in_features, lda, ldw multiples of 4 and 16-byte aligned operands (nfk_linear_tf32x3_supported). */
+int nfk_linear_tf32x3_supported(int64_t lda, int64_t ldw, int32_t in_features);
+int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo, int64_t ldw,
+                      const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy, float* y_hi, float* y_lo,
+                      int64_t lds, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
+                      int32_t out_features, void* stream);
+/* hi[n, j], lo[n, j] = split of pre(x[n*ldx + (cols ? cols[j] : j)]), pre = relu if `relu`.  Produces the operand pairs
+ * nfk_linear_tf32x3 consumes (activations entering a layer chain, and weights once per parameter update). */
+int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_cols, int relu, float* hi, float* lo,
+                   int64_t ldo, int64_t n_rows, void* stream);
+
 /* ---- row-wise elementwise transforms -------------------------------------------------------------------- */
 /* out[n, j] = x[n*ldx + cols[j]] (identity_split gather, coupling.py:82; Permutation._permute,
  * permutations.py:27-39).  Bit-exact copy. */

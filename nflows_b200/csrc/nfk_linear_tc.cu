@@ -1,0 +1,427 @@
+// Dense layer on the 5th-generation tensor cores (tcgen05) with fp32-equivalent operand precision.
+//
+//   Y = post(A W^T + b) + R           A: [n_rows, K]   W: [N, K] (nn.Linear layout)   fp32 accumulate in TMEM
+//
+// PyTorch's reference GEMM is true fp32 (allow_tf32=False), and a single TF32 pass misses the 1e-5 parity bar by
+// two orders of magnitude.  So every operand is carried as a split pair
+//   a = a_hi + a_lo,  a_hi = rna_tf32(a) (10-bit mantissa, stored in an fp32 container),  a_lo = a - a_hi (exact)
+// and each K-step issues three kind::tf32 MMAs into the same accumulator:  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// (the dropped a_lo*w_lo term is ~2^-22 relative).  Producers of activations write the split pair in their
+// epilogue, weights are split once when a module's parameters change.
+//
+// Kernel shape (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor 2-D boxes {32 k, 128 rows} / {32 k, BN rows}, SWIZZLE_128B,
+//                                out-of-bounds rows/columns zero-filled by the TMA unit (no padding anywhere)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 8, K-major smem descriptors)
+//   warps 2-5: epilogue       -- tcgen05.ld 32 lanes x 16 columns -> bias / relu / residual -> global stores of the
+//                                fp32 result and/or the split pair consumed by the next layer
+//   smem ring: 2 stages x (A_hi, A_lo, W_hi, W_lo) = 2 x 96 KB;  TMEM: 2 accumulators x 256 columns, so the epilogue
+//   of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "nfk_common.cuh"
+
+namespace nfk {
+namespace tc {
+
+constexpr int BM = 128;            // rows per tile = TMEM lanes
+constexpr int BN_MAX = 256;        // columns per tile (runtime BN <= BN_MAX, multiple of 16)
+constexpr int BK = 32;             // fp32 elements per K-slab = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int THREADS = 192;
+constexpr int A_BYTES = BM * BK * 4;             // 16 KB
+constexpr int B_BYTES = BN_MAX * BK * 4;         // 32 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 128 B = 1024 B)
+// | [46,48) version=1 (sm_100) | [61,64) layout 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Params {
+    const float* bias;       // [N] or null
+    const float* residual;   // [n_rows, ldr] or null
+    float* y;                // fp32 result or null
+    float* y_hi;             // split pair of pre(y) for the next layer, or null
+    float* y_lo;
+    int64_t ldr, ldy, lds;
+    int64_t n_rows;
+    int K, N, BN;
+    int relu_out;            // relu applied to (acc + bias) before the residual add / store
+    int split_relu;          // relu applied before splitting (the next layer consumes relu(y))
+    int num_m_tiles, num_n_tiles;
+};
+
+__device__ __forceinline__ float tf32_hi(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                     const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;                // 8-byte mbarriers
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
+    const uint32_t bar_tfull = bars + 16 * STAGES, bar_tempty = bars + 16 * STAGES + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_k = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================================= TMA producer
+        if (lane == 0) {
+            const uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)p.BN * BK * 4u;
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t % p.num_m_tiles) * BM;
+                const int n0 = (t / p.num_m_tiles) * p.BN;
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    mbar_expect_tx(full, tx_bytes);
+                    tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
+                    tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
+                    tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n0);
+                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================= MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN_MAX;
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(bar_full + 8 * stage, phase);                // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
+                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 8; ++kk) {                  // UMMA K = 8 tf32 = 32 bytes = +2 in desc units
+                        const uint64_t adv = (uint64_t)(kk * 2);
+                        umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (ks | kk) != 0);
+                        umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                    }
+                    umma_commit(bar_empty + 8 * stage);                    // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);                          // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================================= epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32)
+        const int q = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        const bool vec_y = p.y && (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const bool vec_s = p.y_hi && (p.lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y_hi) & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.y_lo) & 15) == 0);
+        const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int64_t row = (int64_t)(t % p.num_m_tiles) * BM + q * 32 + lane;
+            const int n0 = (t / p.num_m_tiles) * p.BN;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX;
+            const bool row_ok = row < p.n_rows;
+            for (int c = 0; c < p.BN; c += 16) {
+                uint32_t raw[16];
+                __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge after the predicated body
+                tmem_ld16(taddr + c, raw);
+                tmem_ld_wait();
+                const int col0 = n0 + c;
+                if (row_ok && col0 < p.N) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float x = __uint_as_float(raw[j]);
+                    if (p.bias && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+                    if (p.relu_out) x = fmaxf(x, 0.0f);
+                    v[j] = x;
+                }
+                const bool full16 = col0 + 16 <= p.N;
+                if (p.residual) {
+                    const float* rp = p.residual + row * p.ldr + col0;
+                    if (vec_r && full16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4 r4 = *reinterpret_cast<const float4*>(rp + 4 * j);
+                            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) v[j] += rp[j];
+                    }
+                }
+                if (p.y) {
+                    float* yp = p.y + row * p.ldy + col0;
+                    if (vec_y && full16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) yp[j] = v[j];
+                    }
+                }
+                if (p.y_hi) {
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float x = p.split_relu ? fmaxf(v[j], 0.0f) : v[j];
+                        hi[j] = tf32_hi(x);
+                        lo[j] = x - hi[j];
+                    }
+                    float* hp = p.y_hi + row * p.lds + col0;
+                    float* lp = p.y_lo + row * p.lds + col0;
+                    if (vec_s && full16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            *reinterpret_cast<float4*>(hp + 4 * j) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            *reinterpret_cast<float4*>(lp + 4 * j) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) { hp[j] = hi[j]; lp[j] = lo[j]; }
+                    }
+                }
+                }
+            }
+            __syncwarp();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------- fp32 -> (hi, lo) split, optional column gather / relu
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ldx,
+                                                         const int32_t* __restrict__ cols, int n_cols, int relu,
+                                                         float* __restrict__ hi, float* __restrict__ lo, int64_t ldo,
+                                                         int64_t n_rows) {
+    const int64_t total = n_rows * n_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n_cols;
+        const int j = (int)(i - r * n_cols);
+        float v = x[r * ldx + (cols ? __ldg(cols + j) : j)];
+        if (relu) v = fmaxf(v, 0.0f);
+        const float h = tf32_hi(v);
+        hi[r * ldo + j] = h;
+        lo[r * ldo + j] = v - h;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int K, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return NFK_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace tc
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_cols, int relu, float* hi,
+                              float* lo, int64_t ldo, int64_t n_rows, void* stream) {
+    NFK_REQUIRE(n_rows >= 0 && n_cols >= 0, "bad sizes");
+    if (n_rows == 0 || n_cols == 0) return NFK_OK;
+    NFK_REQUIRE(x && hi && lo, "NULL pointer");
+    int64_t blocks = (n_rows * n_cols + 255) / 256;
+    int grid = (int)(blocks > 148 * 32 ? 148 * 32 : blocks);
+    tc::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, cols, n_cols, relu, hi, lo, ldo, n_rows);
+    return check_launch("split_tf32_kernel");
+}
+
+extern "C" int nfk_linear_tf32x3_supported(int64_t lda, int64_t ldw, int32_t in_features) {
+    return (in_features >= 4 && in_features % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0) ? 1 : 0;
+}
+
+extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo,
+                                 int64_t ldw, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
+                                 float* y_hi, float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
+                                 int32_t in_features, int32_t out_features, void* stream) {
+    NFK_REQUIRE(n_rows >= 0 && in_features >= 1 && out_features >= 1, "bad sizes");
+    if (n_rows == 0) return NFK_OK;
+    NFK_REQUIRE(a_hi && a_lo && w_hi && w_lo, "NULL operand pointer");
+    NFK_REQUIRE(Y || (y_hi && y_lo), "no output requested");
+    NFK_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "y_hi and y_lo must be given together");
+    NFK_REQUIRE(nfk_linear_tf32x3_supported(lda, ldw, in_features), "tf32x3 path needs in_features, lda, ldw multiples of 4");
+    NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(w_hi) && aligned16(w_lo), "operands must be 16-byte aligned");
+    NFK_REQUIRE(n_rows < (1ll << 31), "n_rows too large for one launch");
+
+    tc::Params p;
+    p.bias = bias; p.residual = R; p.y = Y; p.y_hi = y_hi; p.y_lo = y_lo;
+    p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
+    p.relu_out = relu_out; p.split_relu = split_relu;
+    p.num_n_tiles = (out_features + tc::BN_MAX - 1) / tc::BN_MAX;
+    int bn = (out_features + p.num_n_tiles - 1) / p.num_n_tiles;
+    bn = (bn + 15) / 16 * 16;
+    p.BN = bn;
+    p.num_n_tiles = (out_features + bn - 1) / bn;
+    p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
+
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    int rc;
+    if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, in_features, lda, tc::BM))) return rc;
+    if ((rc = tc::make_map(&ma_lo, a_lo, n_rows, in_features, lda, tc::BM))) return rc;
+    if ((rc = tc::make_map(&mw_hi, w_hi, out_features, in_features, ldw, bn))) return rc;
+    if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn))) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < tc::sm_count() ? tiles : tc::sm_count();
+    tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    return check_launch("linear_tf32x3_kernel");
+}

@@ -1,0 +1,99 @@
+"""Execution of dense-layer chains (conditioner networks, folded affine maps) on the native GEMM kernels.
+
+Two kernels implement the same contract (fp32-equivalent products, fp32 accumulation):
+  * "tc"   -- `nfk_linear_tf32x3`: tcgen05 tensor cores, operands carried as (hi, lo) TF32 split pairs; the default.
+  * "simt" -- `nfk_linear`: FP32 FFMA pipe; used for shapes the TMA path cannot address (in_features not a multiple
+              of 4) and selectable with NFLOWS_B200_GEMM=simt for A/B comparisons.
+Both are CUDA kernels of this library; there is no PyTorch/cuBLAS path here."""
+import os
+
+from . import kernels as K
+
+_SPLIT_CACHE = {}
+
+
+def backend():
+    return os.environ.get("NFLOWS_B200_GEMM", "tc")
+
+
+def split_weight(weight):
+    """(hi, lo) pair of a weight matrix, cached until the parameter is modified."""
+    w = weight.detach()
+    key = id(weight)
+    sig = (w.data_ptr(), w._version, str(w.device), tuple(w.shape))
+    hit = _SPLIT_CACHE.get(key)
+    if hit is None or hit[0] != sig:
+        if not w.is_contiguous():
+            w = w.contiguous()
+        hit = (sig, K.split_tf32(w), weight)
+        _SPLIT_CACHE[key] = hit
+        if len(_SPLIT_CACHE) > 4096:
+            _SPLIT_CACHE.pop(next(iter(_SPLIT_CACHE)))
+    return hit[1]
+
+
+def chain_uses_tc(chain, first_in_features):
+    if backend() != "tc":
+        return False
+    k = first_in_features
+    for weight, _, _, _, _ in chain:
+        if weight.shape[1] != k or not K.tf32x3_supported(k, weight.stride(0), k):
+            return False
+        k = weight.shape[0]
+    return True
+
+
+class ChainState:
+    """Activation between two layers: fp32 tensor (`raw`) and/or the split pair the next tensor-core layer consumes."""
+
+    def __init__(self, raw=None, pair=None):
+        self.raw, self.pair = raw, pair
+
+
+def run_trunk(chain, x, id_cols, use_tc):
+    """All layers of `chain` but the last, on the identity columns of x.  Returns the ChainState feeding the last layer."""
+    body = chain[:-1]
+    last_relu_in = chain[-1][2]
+    if use_tc:
+        state = ChainState(pair=K.split_tf32(x, id_cols, relu=body[0][2] if body else last_relu_in))
+        skip_src = None
+        for i, (weight, bias, relu_in, relu_out, residual) in enumerate(body):
+            nxt_relu_in = chain[i + 1][2]
+            need_raw = i + 2 < len(chain) and chain[i + 2][4] == "skip"
+            res = skip_src if residual == "skip" else None
+            y, pair = K.linear_tf32x3(state.pair, split_weight(weight), bias.detach() if bias is not None else None,
+                                      residual=res, relu_out=relu_out, want_y=need_raw, want_split=True,
+                                      split_relu=nxt_relu_in)
+            if need_raw:
+                skip_src = y
+            state = ChainState(raw=y, pair=pair)
+        return state
+    hidden = K.gather_cols(x, id_cols)
+    branch = None
+    for weight, bias, relu_in, relu_out, residual in body:
+        b = bias.detach() if bias is not None else None
+        if residual == "skip":
+            hidden = K.linear(branch, weight.detach(), b, residual=hidden, relu_in=relu_in, relu_out=relu_out, out=hidden)
+        elif relu_in:   # first layer of a residual block: keep its input for the skip connection
+            branch = K.linear(hidden, weight.detach(), b, relu_in=True, relu_out=relu_out)
+        else:
+            hidden = K.linear(hidden, weight.detach(), b, relu_in=relu_in, relu_out=relu_out)
+    return ChainState(raw=hidden)
+
+
+def run_last(chain, state, r0, r1, use_tc):
+    """Last layer of the chain on rows [r0, r1) of the trunk output -> fp32 conditioner output."""
+    weight, bias, relu_in, relu_out, _ = chain[-1]
+    b = bias.detach() if bias is not None else None
+    if use_tc:
+        pair = (state.pair[0][r0:r1], state.pair[1][r0:r1])
+        return K.linear_tf32x3(pair, split_weight(weight), b, relu_out=relu_out, want_y=True)[0]
+    return K.linear(state.raw[r0:r1], weight.detach(), b, relu_in=relu_in, relu_out=relu_out)
+
+
+def affine_map(x, weight, bias):
+    """y = x @ weight.T + bias for a folded ActNorm/Permutation/LU run."""
+    k = x.shape[1]
+    if backend() == "tc" and K.tf32x3_supported(x.stride(0), weight.stride(0), k):
+        return K.linear_tf32x3(K.split_tf32(x), split_weight(weight), bias, want_y=True)[0]
+    return K.linear(x, weight, bias)

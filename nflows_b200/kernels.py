@@ -151,3 +151,41 @@ def raise_for_flags(flags):
         raise InputOutsideDomain()
     if v & 2:
         raise AssertionError("rational-quadratic spline inverse: negative discriminant")
+
+
+# ---- split-TF32 tensor-core dense layers ------------------------------------------------------------------------------
+def split_tf32(x, cols_i32=None, relu=False):
+    """(hi, lo) operand pair of pre(x[:, cols]) for `linear_tf32x3`."""
+    _rows2d(x, "x")
+    n = x.shape[0]
+    c = x.shape[1] if cols_i32 is None else cols_i32.numel()
+    hi = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    lo = torch.empty_like(hi)
+    N.check(N.lib().nfk_split_tf32(x.data_ptr(), x.stride(0), N.ptr(cols_i32), c, int(relu), hi.data_ptr(), lo.data_ptr(),
+                                   hi.stride(0), n, N.stream()))
+    return hi, lo
+
+
+def tf32x3_supported(lda, ldw, in_features):
+    return bool(N.load().nfk_linear_tf32x3_supported(int(lda), int(ldw), int(in_features)))
+
+
+def linear_tf32x3(a_pair, w_pair, bias=None, residual=None, relu_out=False, want_y=True, want_split=False,
+                  split_relu=False):
+    """tcgen05 dense layer on split operands.  Returns (y or None, (y_hi, y_lo) or None)."""
+    a_hi, a_lo = a_pair
+    w_hi, w_lo = w_pair
+    n, k = a_hi.shape
+    o = w_hi.shape[0]
+    dev = a_hi.device
+    y = torch.empty(n, o, dtype=torch.float32, device=dev) if want_y else None
+    pair = (torch.empty(n, o, dtype=torch.float32, device=dev), torch.empty(n, o, dtype=torch.float32, device=dev)) \
+        if want_split else None
+    if bias is not None and not bias.is_contiguous():
+        bias = bias.contiguous()
+    N.check(N.lib().nfk_linear_tf32x3(
+        a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N.ptr(bias),
+        N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y), y.stride(0) if y is not None else 0,
+        N.ptr(pair[0]) if pair else 0, N.ptr(pair[1]) if pair else 0, pair[0].stride(0) if pair else 0, int(relu_out),
+        int(split_relu), n, k, o, N.stream()))
+    return y, pair

@@ -18,6 +18,7 @@ from torch.nn.functional import softplus
 
 from .. import _native as N
 from .. import config
+from .. import dense as D
 from .. import kernels as K
 from . import splines
 from .base import Transform, params_frozen
@@ -113,12 +114,13 @@ class CouplingTransform(Transform):
         chain = net.dense_chain(context) if hasattr(net, "dense_chain") else None
         n_params = self.num_transform_features * self._transform_dim_multiplier()
         trunk_rows = 1 << 15
+        use_tc = chain is not None and D.chain_uses_tc(chain, self.num_identity_features)
         final_rows = self._conditioner_rows(n_params)
         for r0 in range(0, n, trunk_rows):
             r1 = min(n, r0 + trunk_rows)
             xs = inputs[r0:r1]
-            identity = K.gather_cols(xs, id_cols)
             if chain is None:
+                identity = K.gather_cols(xs, id_cols)
                 if context is not None:
                     context_rows = context[r0:r1]
                 else:
@@ -129,20 +131,11 @@ class CouplingTransform(Transform):
                 self._native_epilogue(xs, params.float().contiguous(), t_cols, id_cols, outputs[r0:r1], lad[r0:r1], flags,
                                       inverse)
                 continue
-            hidden = identity
-            for weight, bias, relu_in, relu_out, residual in chain[:-1]:
-                if residual == "skip":
-                    hidden = K.linear(branch, weight.detach(), bias.detach(), residual=hidden, relu_in=relu_in,
-                                      relu_out=relu_out, out=hidden)
-                elif relu_in:   # first layer of a residual block: keep the block input for the skip connection
-                    branch = K.linear(hidden, weight.detach(), bias.detach(), relu_in=True, relu_out=relu_out)
-                else:
-                    hidden = K.linear(hidden, weight.detach(), bias.detach(), relu_in=relu_in, relu_out=relu_out)
-            weight, bias, relu_in, relu_out, _ = chain[-1]
+            state = D.run_trunk(chain, xs, id_cols, use_tc)
             for q0 in range(0, r1 - r0, final_rows):
                 q1 = min(r1 - r0, q0 + final_rows)
                 with K.timed("final_linear", q1 - q0):
-                    params = K.linear(hidden[q0:q1], weight.detach(), bias.detach(), relu_in=relu_in, relu_out=relu_out)
+                    params = D.run_last(chain, state, q0, q1, use_tc)
                 with K.timed("spline_epilogue", q1 - q0):
                     self._native_epilogue(xs[q0:q1], params, t_cols, id_cols, outputs[r0 + q0:r0 + q1],
                                           lad[r0 + q0:r0 + q1], flags, inverse)
