@@ -5,18 +5,25 @@
 // PyTorch's reference GEMM is true fp32 (allow_tf32=False), and a single TF32 pass misses the 1e-5 parity bar by
 // two orders of magnitude.  So every operand is carried as a split pair
 //   a = a_hi + a_lo,  a_hi = rna_tf32(a) (10-bit mantissa, stored in an fp32 container),  a_lo = a - a_hi (exact)
-// and each K-step issues three kind::tf32 MMAs into the same accumulator:  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// and each K-step issues three kind::tf32 MMAs into the same accumulator:  a_lo*w_hi + a_hi*w_lo + a_hi*w_hi
 // (the dropped a_lo*w_lo term is ~2^-22 relative).  Producers of activations write the split pair in their
 // epilogue, weights are split once when a module's parameters change.
 //
-// Kernel shape (one persistent CTA per SM, 192 threads):
+// Accumulation: the tensor core adds into its fp32 accumulator with round-toward-zero, so a long chain of MMAs
+// acquires a bias of ~0.5 ulp per instruction (measured here: 2e-5 relative after the 294 MMAs of K=784, the same
+// effect Ootomo & Yokota 2022 report for Ampere).  The accumulator in TMEM therefore only ever holds a PARTIAL sum
+// over DRAIN_SLABS K-slabs (24 MMAs); the epilogue warps drain it with tcgen05.ld and keep the running sum in
+// registers with round-to-nearest FADDs, while the issuer continues into the other TMEM buffer.
+//
+// Kernel shape (one persistent CTA per SM, 384 threads; setmaxnreg moves registers from warpgroup 0 to 1-2):
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor 2-D boxes {32 k, 128 rows} / {32 k, BN rows}, SWIZZLE_128B,
 //                                out-of-bounds rows/columns zero-filled by the TMA unit (no padding anywhere)
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 8, K-major smem descriptors)
-//   warps 2-5: epilogue       -- tcgen05.ld 32 lanes x 16 columns -> bias / relu / residual -> global stores of the
-//                                fp32 result and/or the split pair consumed by the next layer
-//   smem ring: 2 stages x (A_hi, A_lo, W_hi, W_lo) = 2 x 96 KB;  TMEM: 2 accumulators x 256 columns, so the epilogue
-//   of tile i overlaps the MMAs of tile i+1.
+//   warps 4-11: accumulate/epilogue -- warp w owns TMEM lanes [32(w%4), +32) and column half (w-4)/4 of the tile:
+//                                tcgen05.ld of each partial sum -> 128 running sums per thread in registers; at the end of
+//                                a tile bias / relu / residual -> global stores of the fp32 result and/or the split pair
+//                                consumed by the next layer
+//   smem ring: 2 stages x (A_hi, A_lo, W_hi, W_lo) = 2 x 96 KB;  TMEM: 2 partial accumulators x 256 columns.
 #include <cuda.h>
 
 #include <mutex>
@@ -30,7 +37,9 @@ constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int BN_MAX = 256;        // columns per tile (runtime BN <= BN_MAX, multiple of 16)
 constexpr int BK = 32;             // fp32 elements per K-slab = one 128-byte swizzle row
 constexpr int STAGES = 2;
-constexpr int THREADS = 192;
+constexpr int THREADS = 384;        // warpgroup 0: TMA + MMA warps (2 idle); warpgroups 1-2: accumulate/epilogue
+constexpr int DRAIN_SLABS = 2;       // K-slabs accumulated inside the tensor core before a drain (2 x 32 = K 64)
+constexpr int HALF = BN_MAX / 2;     // columns per epilogue warp
 constexpr int A_BYTES = BM * BK * 4;             // 16 KB
 constexpr int B_BYTES = BN_MAX * BK * 4;         // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
@@ -100,6 +109,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -151,7 +171,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
     }
@@ -160,7 +180,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int num_groups = (num_k + DRAIN_SLABS - 1) / DRAIN_SLABS;     // partial sums per tile
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");     // hand registers to the epilogue warpgroups
     if (warp == 0) {
         // ================================================= TMA producer
         if (lane == 0) {
@@ -189,32 +212,38 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);          // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-                for (int ks = 0; ks < num_k; ++ks) {
-                    mbar_wait(bar_full + 8 * stage, phase);                // TMA bytes have landed
+                for (int g = 0; g < num_groups; ++g) {
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);      // epilogue has drained this partial accumulator
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
-                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+                    const uint32_t d_tmem = tmem_base + acc * BN_MAX;
+                    const int ks_end = min(num_k, (g + 1) * DRAIN_SLABS);
+                    for (int ks = g * DRAIN_SLABS; ks < ks_end; ++ks) {
+                        mbar_wait(bar_full + 8 * stage, phase);            // TMA bytes have landed
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                        const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
+                        const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {                  // UMMA K = 8 tf32 = 32 bytes = +2 in desc units
-                        const uint64_t adv = (uint64_t)(kk * 2);
-                        umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (ks | kk) != 0);
-                        umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
-                        umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                        for (int kk = 0; kk < BK / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes = +2 in desc units
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (ks != g * DRAIN_SLABS) || kk != 0);
+                            umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                            umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                        }
+                        umma_commit(bar_empty + 8 * stage);                // frees the smem slot when the MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(bar_empty + 8 * stage);                    // frees the smem slot when the MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(bar_tfull + 8 * acc);                      // partial sum complete -> drain
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * acc);                          // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+    }
     } else {
-        // ================================================= epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32)
-        const int q = warp & 3;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+        // ================================================= accumulate + epilogue: 8 warps
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;         // column half of the tile
         int acc = 0; uint32_t acc_phase = 0;
         const bool vec_y = p.y && (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
         const bool vec_s = p.y_hi && (p.lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y_hi) & 15) == 0) &&
@@ -222,79 +251,92 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int64_t row = (int64_t)(t % p.num_m_tiles) * BM + q * 32 + lane;
-            const int n0 = (t / p.num_m_tiles) * p.BN;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX;
-            const bool row_ok = row < p.n_rows;
-            for (int c = 0; c < p.BN; c += 16) {
-                uint32_t raw[16];
-                __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge after the predicated body
-                tmem_ld16(taddr + c, raw);
-                tmem_ld_wait();
-                const int col0 = n0 + c;
-                if (row_ok && col0 < p.N) {
-                float v[16];
+            const int n0 = (t / p.num_m_tiles) * p.BN + half * HALF;
+            float sum[HALF];
+            for (int g = 0; g < num_groups; ++g) {
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HALF;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float x = __uint_as_float(raw[j]);
-                    if (p.bias && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
-                    if (p.relu_out) x = fmaxf(x, 0.0f);
-                    v[j] = x;
-                }
-                const bool full16 = col0 + 16 <= p.N;
-                if (p.residual) {
-                    const float* rp = p.residual + row * p.ldr + col0;
-                    if (vec_r && full16) {
+                for (int c = 0; c < HALF; c += 16) {
+                    uint32_t raw[16];
+                    tmem_ld16(taddr + c, raw);
+                    tmem_ld_wait();
+                    if (g == 0) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float4 r4 = *reinterpret_cast<const float4*>(rp + 4 * j);
-                            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
-                        }
+                        for (int j = 0; j < 16; ++j) sum[c + j] = __uint_as_float(raw[j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) v[j] += rp[j];
+                        for (int j = 0; j < 16; ++j) sum[c + j] = __fadd_rn(sum[c + j], __uint_as_float(raw[j]));
                     }
                 }
-                if (p.y) {
-                    float* yp = p.y + row * p.ldy + col0;
-                    if (vec_y && full16) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (row < p.n_rows) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) yp[j] = v[j];
-                    }
-                }
-                if (p.y_hi) {
-                    float hi[16], lo[16];
+                for (int c = 0; c < HALF; c += 16) {
+                    const int col0 = n0 + c;
+                    if (c + half * HALF >= p.BN || col0 >= p.N) continue;
+                    float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const float x = p.split_relu ? fmaxf(v[j], 0.0f) : v[j];
-                        hi[j] = tf32_hi(x);
-                        lo[j] = x - hi[j];
+                        float x = sum[c + j];
+                        if (p.bias && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+                        if (p.relu_out) x = fmaxf(x, 0.0f);
+                        v[j] = x;
                     }
-                    float* hp = p.y_hi + row * p.lds + col0;
-                    float* lp = p.y_lo + row * p.lds + col0;
-                    if (vec_s && full16) {
+                    const bool full16 = col0 + 16 <= p.N;
+                    if (p.residual) {
+                        const float* rp = p.residual + row * p.ldr + col0;
+                        if (vec_r && full16) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            *reinterpret_cast<float4*>(hp + 4 * j) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            *reinterpret_cast<float4*>(lp + 4 * j) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            for (int j = 0; j < 4; ++j) {
+                                float4 r4 = *reinterpret_cast<const float4*>(rp + 4 * j);
+                                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N) v[j] += rp[j];
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) if (col0 + j < p.N) { hp[j] = hi[j]; lp[j] = lo[j]; }
                     }
-                }
+                    if (p.y) {
+                        float* yp = p.y + row * p.ldy + col0;
+                        if (vec_y && full16) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N) yp[j] = v[j];
+                        }
+                    }
+                    if (p.y_hi) {
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = p.split_relu ? fmaxf(v[j], 0.0f) : v[j];
+                            hi[j] = tf32_hi(x);
+                            lo[j] = x - hi[j];
+                        }
+                        float* hp = p.y_hi + row * p.lds + col0;
+                        float* lp = p.y_lo + row * p.lds + col0;
+                        if (vec_s && full16) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                *reinterpret_cast<float4*>(hp + 4 * j) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                                *reinterpret_cast<float4*>(lp + 4 * j) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N) { hp[j] = hi[j]; lp[j] = lo[j]; }
+                        }
+                    }
                 }
             }
             __syncwarp();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 

@@ -28,7 +28,7 @@ def test_linear_simt(cuda_device, n, k, o):
     r = torch.randn(n, o, device=cuda_device, generator=g)
     for relu_in, relu_out, res in ((False, False, None), (True, True, None), (False, False, r)):
         y = K.linear(x, w, b, residual=res, relu_in=relu_in, relu_out=relu_out)
-        assert rel_err(y, reference(x, w, b, res, relu_in, relu_out)) <= 2e-6
+        assert rel_err(y, reference(x, w, b, res, relu_in, relu_out)) <= 8e-6
 
 
 @torch.no_grad()
@@ -46,7 +46,7 @@ def test_linear_tf32x3(cuda_device, n, k, o):
         xp = K.split_tf32(x, relu=relu_in)
         y, pair = K.linear_tf32x3(xp, wp, b, residual=res, relu_out=relu_out, want_y=True, want_split=True, split_relu=True)
         want = reference(x, w, b, res, relu_in, relu_out)
-        assert rel_err(y, want) <= 2e-6, (n, k, o, relu_in, relu_out)
+        assert rel_err(y, want) <= 8e-6, (n, k, o, relu_in, relu_out)
         assert torch.equal(pair[0] + pair[1], y.clamp_min(0))
         # hi part is a TF32 number: low 13 mantissa bits are zero
         assert int((pair[0].view(torch.int32) & 0x1FFF).abs().max()) == 0
@@ -64,4 +64,4 @@ def test_linear_tf32x3_unsupported_shapes_are_rejected(cuda_device):
     with pytest.raises(RuntimeError):
         K.linear_tf32x3(K.split_tf32(x), K.split_tf32(w))
     # ... and the FFMA kernel takes them
-    assert rel_err(K.linear(x, w), x.double() @ w.double().t()) <= 2e-6
+    assert rel_err(K.linear(x, w), x.double() @ w.double().t()) <= 8e-6
