@@ -97,9 +97,28 @@ int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
                       int64_t lds, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
                       int32_t out_features, void* stream);
 /* hi[n, j], lo[n, j] = split of pre(x[n*ldx + (cols ? cols[j] : j)]), pre = relu if `relu`.  Produces the operand pairs
- * nfk_linear_tf32x3 consumes (activations entering a layer chain, and weights once per parameter update). */
+ * nfk_linear_tf32x3 consumes (activations entering a layer chain, and weights once per parameter update).  If copy_dst is
+ * not NULL the raw values are also copied to copy_dst[n*ldc + col] (the identity half of a coupling output). */
 int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_cols, int relu, float* hi, float* lo,
-                   int64_t ldo, int64_t n_rows, void* stream);
+                   int64_t ldo, float* copy_dst, int64_t ldc, int64_t n_rows, void* stream);
+
+/* ---- fused RQ-coupling step ------------------------------------------------------------------------------------ */
+/* Final conditioner layer + spline + scatter + log|det| in ONE tcgen05 kernel: replaces the last F.linear of the
+ * conditioner (nn/nets/resnet.py:99), PiecewiseCouplingTransform._coupling_transform / _piecewise_cdf (coupling.py:279-293,
+ * 549-582), the spline (splines/rational_quadratic.py:13-181) and the transform-half scatter (coupling.py:98).
+ *   a_hi/a_lo  : split pair of the last hidden activation [n_rows, hidden_features]
+ *   wp_hi/wp_lo: split pair of the PACKED final weight [d_t * MP, hidden_features]: row j*MP + k = reference row j*M + k
+ *                for k < M, zero rows for M <= k < MP, MP = nfk_rq_coupling_final_padded_params(num_bins, tails)
+ *   bias_packed: [d_t * MP] packed the same way
+ * Writes y[n, t_cols[j]] for every transformed feature (the caller copies the identity columns, e.g. with the
+ * copy_dst of nfk_split_tf32) and adds the row's log|det| to lad_accum.  nfk_rq_coupling_final_supported says whether an
+ * instance exists for (num_bins, tails, hidden_features, lda); otherwise use nfk_linear* + nfk_rqs_rows. */
+int nfk_rq_coupling_final_supported(int32_t num_bins, int32_t linear_tails, int32_t hidden_features, int64_t lda);
+int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t linear_tails);
+int nfk_rq_coupling_final_tf32x3(const NfkSplineDesc* desc, int inverse, const float* a_hi, const float* a_lo, int64_t lda,
+                                 const float* wp_hi, const float* wp_lo, int64_t ldw, const float* bias_packed,
+                                 int32_t hidden_features, const float* x, int64_t ldx, const int32_t* t_cols, int32_t d_t,
+                                 float* y, int64_t ldy, float* lad_accum, int64_t n_rows, int32_t* flags, void* stream);
 
 /* ---- row-wise elementwise transforms -------------------------------------------------------------------- */
 /* out[n, j] = x[n*ldx + cols[j]] (identity_split gather, coupling.py:82; Permutation._permute,

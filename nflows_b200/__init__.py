@@ -13,6 +13,8 @@ class _Config:
     check_domain = True
     #: upper bound (MiB) for the conditioner-output chunk a coupling keeps in flight; sized to stay in B200's L2
     param_chunk_mib = 64
+    #: run the final conditioner layer and the spline as ONE tensor-core kernel when an instance exists
+    fuse_coupling = True
 
 
 config = _Config()

@@ -24,114 +24,12 @@
 //                                a tile bias / relu / residual -> global stores of the fp32 result and/or the split pair
 //                                consumed by the next layer
 //   smem ring: 2 stages x (A_hi, A_lo, W_hi, W_lo) = 2 x 96 KB;  TMEM: 2 partial accumulators x 256 columns.
-#include <cuda.h>
-
 #include <mutex>
 
-#include "nfk_common.cuh"
+#include "tc_common.cuh"
 
 namespace nfk {
 namespace tc {
-
-constexpr int BM = 128;            // rows per tile = TMEM lanes
-constexpr int BN_MAX = 256;        // columns per tile (runtime BN <= BN_MAX, multiple of 16)
-constexpr int BK = 32;             // fp32 elements per K-slab = one 128-byte swizzle row
-constexpr int STAGES = 2;
-constexpr int THREADS = 384;        // warpgroup 0: TMA + MMA warps (2 idle); warpgroups 1-2: accumulate/epilogue
-constexpr int DRAIN_SLABS = 2;       // K-slabs accumulated inside the tensor core before a drain (2 x 32 = K 64)
-constexpr int HALF = BN_MAX / 2;     // columns per epilogue warp
-constexpr int A_BYTES = BM * BK * 4;             // 16 KB
-constexpr int B_BYTES = BN_MAX * BK * 4;         // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 128 B = 1024 B)
-// | [46,48) version=1 (sm_100) | [61,64) layout 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 
 struct Params {
     const float* bias;       // [N] or null
@@ -146,12 +44,6 @@ struct Params {
     int split_relu;          // relu applied before splitting (the next layer consumes relu(y))
     int num_m_tiles, num_n_tiles;
 };
-
-__device__ __forceinline__ float tf32_hi(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
 
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -223,11 +115,17 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         const uint32_t sa = smem_base + stage * STAGE_BYTES;
                         const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
                         const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+                        // UMMA K = 8 tf32 = 32 bytes = +2 in descriptor units.  The small cross terms go first, while the
+                        // accumulator is still ~2^-11 of its final size, so only the BK/8 main products round at full size.
 #pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes = +2 in desc units
+                        for (int kk = 0; kk < BK / 8; ++kk) {
                             const uint64_t adv = (uint64_t)(kk * 2);
                             umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (ks != g * DRAIN_SLABS) || kk != 0);
                             umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < BK / 8; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);
                             umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                         }
                         umma_commit(bar_empty + 8 * stage);                // frees the smem slot when the MMAs retire
@@ -349,12 +247,14 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ldx,
                                                          const int32_t* __restrict__ cols, int n_cols, int relu,
                                                          float* __restrict__ hi, float* __restrict__ lo, int64_t ldo,
-                                                         int64_t n_rows) {
+                                                         float* __restrict__ copy_dst, int64_t ldc, int64_t n_rows) {
     const int64_t total = n_rows * n_cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n_cols;
         const int j = (int)(i - r * n_cols);
-        float v = x[r * ldx + (cols ? __ldg(cols + j) : j)];
+        const int c = cols ? __ldg(cols + j) : j;
+        float v = x[r * ldx + c];
+        if (copy_dst) copy_dst[r * ldc + c] = v;          // bit-exact pass-through of the identity columns
         if (relu) v = fmaxf(v, 0.0f);
         const float h = tf32_hi(v);
         hi[r * ldo + j] = h;
@@ -380,7 +280,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int K, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int K, int64_t ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -394,7 +294,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int K, in
     return NFK_OK;
 }
 
-static int sm_count() {
+int sm_count() {
     static int n = 0;
     if (!n) {
         int dev = 0;
@@ -411,13 +311,13 @@ static int sm_count() {
 using namespace nfk;
 
 extern "C" int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_cols, int relu, float* hi,
-                              float* lo, int64_t ldo, int64_t n_rows, void* stream) {
+                              float* lo, int64_t ldo, float* copy_dst, int64_t ldc, int64_t n_rows, void* stream) {
     NFK_REQUIRE(n_rows >= 0 && n_cols >= 0, "bad sizes");
     if (n_rows == 0 || n_cols == 0) return NFK_OK;
     NFK_REQUIRE(x && hi && lo, "NULL pointer");
     int64_t blocks = (n_rows * n_cols + 255) / 256;
     int grid = (int)(blocks > 148 * 32 ? 148 * 32 : blocks);
-    tc::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, cols, n_cols, relu, hi, lo, ldo, n_rows);
+    tc::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, cols, n_cols, relu, hi, lo, ldo, copy_dst, ldc, n_rows);
     return check_launch("split_tf32_kernel");
 }
 

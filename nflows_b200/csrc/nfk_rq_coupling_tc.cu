@@ -1,0 +1,304 @@
+// ONE kernel for the dominant step of PiecewiseRationalQuadraticCouplingTransform (coupling.py:279-293, 549-582 +
+// splines/rational_quadratic.py:13-181 in the reference): the final conditioner layer (hidden -> d_t * (3K-1)
+// spline parameters, 86 % of the flow's FLOPs) on tcgen05 tensor cores, with the rational-quadratic spline, the scatter of
+// the transformed features and the per-row log|det| evaluated by the epilogue warps straight from the accumulators.
+// The [B, d_t*M] parameter tensor the reference materialises (37.8 GB per layer at B = 2^20) never exists.
+//
+// Same machinery as nfk_linear_tc.cu (TMA-fed split-TF32 operands, partial sums drained from TMEM into registers);
+// what differs:
+//   * the packed weight has MP = roundup(M, 8) rows per transformed feature (zero padded), so a tile of BN = 2*FPT*MP
+//     columns holds whole features and each accumulate/epilogue thread ends a tile owning ALL parameters of FPT features
+//     of its row in registers (K = 8 bins, linear tails: MP = 24, FPT = 5, BN = 240);
+//   * a CTA walks the N-tiles of one 128-row block consecutively, so every thread keeps the running log|det| of its row
+//     in a register and the row is finished (y written, lad_accum updated, deterministically) when the CTA moves on.
+#include "rq_spline.cuh"
+#include "tc_common.cuh"
+
+namespace nfk {
+namespace tc {
+
+struct FusedParams {
+    const float* bias;      // [d_t * MP] packed like the weight rows, zero padded
+    const float* x;         // coupling input [n_rows, ldx]
+    float* y;               // coupling output [n_rows, ldy]; identity columns are written by the caller
+    const int32_t* t_cols;  // [d_t] column of transformed feature j
+    float* lad_accum;       // [n_rows] running log|det| (read-modify-write) or null
+    int32_t* flags;
+    int64_t ldx, ldy, n_rows;
+    int K;                  // hidden features (GEMM reduction length)
+    int d_t;
+    int num_m_tiles, num_n_tiles;
+    int inverse;
+    SplineParams sp;
+};
+
+template <int NB, bool TAILS>
+struct FusedCfg {
+    static constexpr int M = TAILS ? 3 * NB - 1 : 3 * NB + 1;   // parameters per feature
+    static constexpr int MP = (M + 7) / 8 * 8;                  // padded
+    static constexpr int FPT = 128 / MP;                        // features per thread per tile
+    static constexpr int HALF_COLS = FPT * MP;                  // columns per accumulate/epilogue warp
+    static constexpr int BN = 2 * HALF_COLS;                    // tile columns (multiple of 16, <= 256)
+    static_assert(FPT >= 1 && BN <= BN_MAX && BN % 16 == 0, "unsupported bin count for the fused kernel");
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+template <int NB, bool TAILS>
+__global__ void __launch_bounds__(THREADS, 1)
+rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                         const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                         const FusedParams p) {
+    using Cfg = FusedCfg<NB, TAILS>;
+    constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HALF_COLS, BN = Cfg::BN;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
+    const uint32_t bar_tfull = bars + 16 * STAGES, bar_tempty = bars + 16 * STAGES + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+    float* s_lad = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);       // [128] half-1 partial log|det|
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = (p.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+        if (warp == 0) {
+            // ================================================= TMA producer
+            if (lane == 0) {
+                constexpr uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)BN * BK * 4u;
+                int stage = 0; uint32_t phase = 0;
+                for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
+                    for (int n = 0; n < p.num_n_tiles; ++n) {
+                        for (int ks = 0; ks < num_k; ++ks) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            const uint32_t full = bar_full + 8 * stage;
+                            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                            mbar_expect_tx(full, tx_bytes);
+                            tma_load_2d(sa, &map_a_hi, full, ks * BK, m * BM);
+                            tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m * BM);
+                            tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n * BN);
+                            tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n * BN);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ================================================= MMA issuer (one thread): one partial sum per K-slab
+            if (lane == 0) {
+                const uint32_t idesc = make_idesc(BN);
+                int stage = 0; uint32_t phase = 0;
+                int acc = 0; uint32_t acc_phase = 0;
+                for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
+                    for (int n = 0; n < p.num_n_tiles; ++n) {
+                        for (int ks = 0; ks < num_k; ++ks) {
+                            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                            mbar_wait(bar_full + 8 * stage, phase);
+                            tc_fence_after();
+                            const uint32_t d_tmem = tmem_base + acc * BN_MAX;
+                            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
+                            const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < BK / 8; ++kk) {          // cross terms first (see nfk_linear_tc.cu)
+                                const uint64_t adv = (uint64_t)(kk * 2);
+                                umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, kk != 0);
+                                umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                            }
+#pragma unroll
+                            for (int kk = 0; kk < BK / 8; ++kk) {
+                                const uint64_t adv = (uint64_t)(kk * 2);
+                                umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                            }
+                            umma_commit(bar_empty + 8 * stage);
+                            umma_commit(bar_tfull + 8 * acc);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+        // ================================================= accumulate + spline epilogue: 8 warps
+        const int q = warp & 3;                   // TMEM lane quarter
+        const int half = (warp - 4) >> 2;         // which FPT features of the tile
+        int acc = 0; uint32_t acc_phase = 0;
+        int flag = 0;
+        for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
+            const int64_t row = (int64_t)m * BM + q * 32 + lane;
+            const bool row_ok = row < p.n_rows;
+            float lad_row = 0.0f;
+            for (int n = 0; n < p.num_n_tiles; ++n) {
+                const int j0 = (n * 2 + half) * FPT;                       // first feature this thread owns in this tile
+                float xin[FPT];
+                int col[FPT];
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) {
+                    const bool ok = row_ok && (j0 + f < p.d_t);
+                    col[f] = ok ? __ldg(p.t_cols + j0 + f) : 0;
+                    xin[f] = ok ? __ldg(p.x + row * p.ldx + col[f]) : 0.0f;
+                }
+                float sum[HC];
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HC;
+#pragma unroll
+                    for (int c = 0; c < HC; c += 8) {
+                        uint32_t raw[8];
+                        tmem_ld8(taddr + c, raw);
+                        tmem_ld_wait();
+                        if (ks == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) sum[c + i] = __uint_as_float(raw[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) sum[c + i] = __fadd_rn(sum[c + i], __uint_as_float(raw[i]));
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                // ---- spline on the FPT features held in registers
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) {
+                    const int j = j0 + f;
+                    if (row_ok && j < p.d_t) {
+                        const float* bj = p.bias + (int64_t)j * MP;
+                        float w[NB], h[NB], d[NB + 1];
+#pragma unroll
+                        for (int k = 0; k < NB; ++k) {
+                            w[k] = sum[f * MP + k] + __ldg(bj + k);
+                            h[k] = sum[f * MP + NB + k] + __ldg(bj + NB + k);
+                        }
+                        if (TAILS) {
+                            d[0] = p.sp.edge_ud;
+                            d[NB] = p.sp.edge_ud;
+#pragma unroll
+                            for (int k = 1; k < NB; ++k) d[k] = sum[f * MP + 2 * NB + k - 1] + __ldg(bj + 2 * NB + k - 1);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k <= NB; ++k) d[k] = sum[f * MP + 2 * NB + k] + __ldg(bj + 2 * NB + k);
+                        }
+                        float yy, ll;
+                        rqs_eval<NB>(p.sp, p.inverse != 0, xin[f], w, h, d, yy, ll, flag);
+                        p.y[row * p.ldy + col[f]] = yy;
+                        lad_row += ll;
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- finish the row block: lad_accum[row] += (half 0 partial) + (half 1 partial), fixed order
+            if (p.lad_accum) {
+                if (half == 1) s_lad[q * 32 + lane] = lad_row;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0 && row_ok) p.lad_accum[row] += lad_row + s_lad[q * 32 + lane];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        }
+        if (flag && p.flags) atomicOr(p.flags, flag);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <int NB, bool TAILS>
+static int launch_fused(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo, int64_t ldw,
+                        FusedParams& p, cudaStream_t st) {
+    using Cfg = FusedCfg<NB, TAILS>;
+    const int packed_rows = p.d_t * Cfg::MP;
+    CUtensorMap mw_hi, mw_lo;
+    int rc;
+    if ((rc = make_map(&mw_hi, w_hi, packed_rows, p.K, ldw, Cfg::BN))) return rc;
+    if ((rc = make_map(&mw_lo, w_lo, packed_rows, p.K, ldw, Cfg::BN))) return rc;
+    p.num_n_tiles = (p.d_t + 2 * Cfg::FPT - 1) / (2 * Cfg::FPT);
+    constexpr int smem = SMEM_BYTES + 512;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int grid = p.num_m_tiles < sm_count() ? p.num_m_tiles : sm_count();
+    rq_coupling_final_kernel<NB, TAILS><<<grid, THREADS, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    return check_launch("rq_coupling_final_kernel");
+}
+
+}  // namespace tc
+}  // namespace nfk
+
+using namespace nfk;
+
+extern "C" int nfk_rq_coupling_final_supported(int32_t num_bins, int32_t linear_tails, int32_t hidden_features, int64_t lda) {
+    const bool bins_ok = (num_bins == 8 || num_bins == 10 || num_bins == 4 || num_bins == 16);
+    return (bins_ok && hidden_features >= 4 && hidden_features % 4 == 0 && lda % 4 == 0) ? 1 : 0;
+}
+
+extern "C" int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t linear_tails) {
+    const int m = linear_tails ? 3 * num_bins - 1 : 3 * num_bins + 1;
+    return (m + 7) / 8 * 8;
+}
+
+extern "C" int nfk_rq_coupling_final_tf32x3(const NfkSplineDesc* desc, int inverse, const float* a_hi, const float* a_lo,
+                                            int64_t lda, const float* wp_hi, const float* wp_lo, int64_t ldw,
+                                            const float* bias_packed, int32_t hidden_features, const float* x, int64_t ldx,
+                                            const int32_t* t_cols, int32_t d_t, float* y, int64_t ldy, float* lad_accum,
+                                            int64_t n_rows, int32_t* flags, void* stream) {
+    tc::FusedParams p;
+    int rc = make_spline_params(desc, &p.sp);
+    if (rc) return rc;
+    NFK_REQUIRE(n_rows >= 0 && d_t >= 1 && hidden_features >= 1, "bad sizes");
+    if (n_rows == 0) return NFK_OK;
+    NFK_REQUIRE(a_hi && a_lo && wp_hi && wp_lo && bias_packed && x && t_cols && y, "NULL pointer");
+    NFK_REQUIRE(nfk_rq_coupling_final_supported(desc->num_bins, desc->linear_tails, hidden_features, lda) && ldw % 4 == 0,
+                "fused coupling kernel does not take num_bins=%d hidden=%d", desc->num_bins, hidden_features);
+    NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(wp_hi) && aligned16(wp_lo), "operands must be 16-byte aligned");
+    NFK_REQUIRE(x != y, "y must not alias x");
+    NFK_REQUIRE(n_rows < (1ll << 31), "n_rows too large for one launch");
+    p.bias = bias_packed; p.x = x; p.y = y; p.t_cols = t_cols; p.lad_accum = lad_accum; p.flags = flags;
+    p.ldx = ldx; p.ldy = ldy; p.n_rows = n_rows; p.K = hidden_features; p.d_t = d_t; p.inverse = inverse;
+    p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
+    CUtensorMap ma_hi, ma_lo;
+    if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, hidden_features, lda, tc::BM))) return rc;
+    if ((rc = tc::make_map(&ma_lo, a_lo, n_rows, hidden_features, lda, tc::BM))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tails = desc->linear_tails != 0;
+#define NFK_FUSED(NB)                                                                                       \
+    return tails ? tc::launch_fused<NB, true>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st)                        \
+                 : tc::launch_fused<NB, false>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st)
+    switch (desc->num_bins) {
+        case 4: NFK_FUSED(4);
+        case 8: NFK_FUSED(8);
+        case 10: NFK_FUSED(10);
+        case 16: NFK_FUSED(16);
+    }
+#undef NFK_FUSED
+    return fail(NFK_E_UNSUPPORTED, "num_bins=%d has no fused kernel instance", desc->num_bins);
+}

@@ -9,7 +9,7 @@
 
 namespace nfk {
 
-static int make_spline_params(const NfkSplineDesc* d, SplineParams* p) {
+int make_spline_params(const NfkSplineDesc* d, SplineParams* p) {
     if (!d) return fail(NFK_E_INVALID, "spline desc is NULL");
     const int K = d->num_bins;
     if (K < 1 || K > NFK_MAX_BINS) return fail(NFK_E_INVALID, "num_bins=%d outside [1,%d]", K, NFK_MAX_BINS);

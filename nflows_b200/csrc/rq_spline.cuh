@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/nfk.h"
+
 namespace nfk {
 
 struct SplineParams {        // derived on the host in double precision, rounded once to fp32 (like the
@@ -27,6 +29,9 @@ struct SplineParams {        // derived on the host in double precision, rounded
     float edge_ud;           // float(log(exp(1-min_d)-1)): boundary unnormalised derivative for linear tails
     float knot_eps;          // 1e-6f, searchsorted eps
 };
+
+// host: derive the fp32 constants from the descriptor (nfk_spline.cu)
+int make_spline_params(const NfkSplineDesc* d, SplineParams* p);
 
 __device__ __forceinline__ float softplus_torch(float x, float beta, float inv_beta) {
     // F.softplus(x, beta, threshold=20): x*beta > 20 ? x : log1p(exp(x*beta))/beta
@@ -73,7 +78,7 @@ __device__ __forceinline__ void rqs_eval(const SplineParams& p, bool inverse, fl
     }
 
     // running prefix sums -> knots; select the bin on the fly
-    const float q = inverse ? x : x;
+    const float q = x;
     float cum_w = 0.0f, cum_h = 0.0f;
     float kw_lo = p.left, kh_lo = p.bottom;              // knot k
     float b_cw = p.left, b_ch = p.bottom, b_w = 1.0f, b_h = 1.0f;

@@ -50,12 +50,14 @@ class ChainState:
         self.raw, self.pair = raw, pair
 
 
-def run_trunk(chain, x, id_cols, use_tc):
-    """All layers of `chain` but the last, on the identity columns of x.  Returns the ChainState feeding the last layer."""
+def run_trunk(chain, x, id_cols, use_tc, copy_identity_to=None):
+    """All layers of `chain` but the last, on the identity columns of x.  Returns the ChainState feeding the last layer.
+    copy_identity_to: coupling output whose identity columns are filled on the way (tensor-core path only)."""
     body = chain[:-1]
     last_relu_in = chain[-1][2]
     if use_tc:
-        state = ChainState(pair=K.split_tf32(x, id_cols, relu=body[0][2] if body else last_relu_in))
+        state = ChainState(pair=K.split_tf32(x, id_cols, relu=body[0][2] if body else last_relu_in,
+                                             copy_to=copy_identity_to))
         skip_src = None
         for i, (weight, bias, relu_in, relu_out, residual) in enumerate(body):
             nxt_relu_in = chain[i + 1][2]
@@ -97,3 +99,26 @@ def affine_map(x, weight, bias):
     if backend() == "tc" and K.tf32x3_supported(x.stride(0), weight.stride(0), k):
         return K.linear_tf32x3(K.split_tf32(x), split_weight(weight), bias, want_y=True)[0]
     return K.linear(x, weight, bias)
+
+
+_PACK_CACHE = {}
+
+
+def pack_final_spline(weight, bias, d_t, m, mp):
+    """Packed operands of the fused coupling kernel: rows regrouped to `mp` per transformed feature (zero padded), split
+    into the (hi, lo) pair; bias packed the same way.  Cached until weight or bias is modified."""
+    w, b = weight.detach(), bias.detach()
+    key = id(weight)
+    sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, str(w.device), d_t, m, mp)
+    hit = _PACK_CACHE.get(key)
+    if hit is None or hit[0] != sig:
+        k = w.shape[1]
+        wp = w.new_zeros(d_t, mp, k)
+        wp[:, :m, :] = w.reshape(d_t, m, k)
+        bp = b.new_zeros(d_t, mp)
+        bp[:, :m] = b.reshape(d_t, m)
+        hit = (sig, K.split_tf32(wp.reshape(d_t * mp, k)), bp.reshape(-1).contiguous(), weight)
+        _PACK_CACHE[key] = hit
+        if len(_PACK_CACHE) > 1024:
+            _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
+    return hit[1], hit[2]

@@ -154,15 +154,16 @@ def raise_for_flags(flags):
 
 
 # ---- split-TF32 tensor-core dense layers ------------------------------------------------------------------------------
-def split_tf32(x, cols_i32=None, relu=False):
-    """(hi, lo) operand pair of pre(x[:, cols]) for `linear_tf32x3`."""
+def split_tf32(x, cols_i32=None, relu=False, copy_to=None):
+    """(hi, lo) operand pair of pre(x[:, cols]) for `linear_tf32x3`; optionally copies x[:, cols] into copy_to[:, cols]."""
     _rows2d(x, "x")
     n = x.shape[0]
     c = x.shape[1] if cols_i32 is None else cols_i32.numel()
     hi = torch.empty(n, c, dtype=torch.float32, device=x.device)
     lo = torch.empty_like(hi)
     N.check(N.lib().nfk_split_tf32(x.data_ptr(), x.stride(0), N.ptr(cols_i32), c, int(relu), hi.data_ptr(), lo.data_ptr(),
-                                   hi.stride(0), n, N.stream()))
+                                   hi.stride(0), N.ptr(copy_to), copy_to.stride(0) if copy_to is not None else 0, n,
+                                   N.stream()))
     return hi, lo
 
 
@@ -189,3 +190,21 @@ def linear_tf32x3(a_pair, w_pair, bias=None, residual=None, relu_out=False, want
         N.ptr(pair[0]) if pair else 0, N.ptr(pair[1]) if pair else 0, pair[0].stride(0) if pair else 0, int(relu_out),
         int(split_relu), n, k, o, N.stream()))
     return y, pair
+
+
+def rq_coupling_final_supported(num_bins, tails, hidden, lda):
+    return bool(N.load().nfk_rq_coupling_final_supported(int(num_bins), 1 if tails == "linear" else 0, int(hidden), int(lda)))
+
+
+def rq_coupling_final_padded_params(num_bins, tails):
+    return int(N.load().nfk_rq_coupling_final_padded_params(int(num_bins), 1 if tails == "linear" else 0))
+
+
+def rq_coupling_final(desc, inverse, a_pair, wp_pair, bias_packed, x, t_cols, y, lad_accum, flags):
+    """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel)."""
+    a_hi, a_lo = a_pair
+    N.check(N.lib().nfk_rq_coupling_final_tf32x3(
+        ctypes.byref(desc), int(inverse), a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), wp_pair[0].data_ptr(),
+        wp_pair[1].data_ptr(), wp_pair[0].stride(0), bias_packed.data_ptr(), a_hi.shape[1], x.data_ptr(), x.stride(0),
+        t_cols.data_ptr(), t_cols.numel(), y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
+    return y

@@ -116,6 +116,15 @@ class CouplingTransform(Transform):
         trunk_rows = 1 << 15
         use_tc = chain is not None and D.chain_uses_tc(chain, self.num_identity_features)
         final_rows = self._conditioner_rows(n_params)
+        if use_tc and self._fused_final_ready(chain):
+            # the north-star shape: trunk GEMMs, then ONE kernel = final layer + spline + scatter + log|det|
+            block = 1 << 18
+            for r0 in range(0, n, block):
+                r1 = min(n, r0 + block)
+                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, copy_identity_to=outputs[r0:r1])
+                with K.timed("rq_coupling_final", r1 - r0):
+                    self._fused_final(chain, state, inputs[r0:r1], t_cols, outputs[r0:r1], lad[r0:r1], flags, inverse)
+            return outputs
         for r0 in range(0, n, trunk_rows):
             r1 = min(n, r0 + trunk_rows)
             xs = inputs[r0:r1]
@@ -143,6 +152,9 @@ class CouplingTransform(Transform):
 
     def _native_epilogue(self, x, params, t_cols, id_cols, out, lad, flags, inverse):
         raise NotImplementedError()
+
+    def _fused_final_ready(self, chain):
+        return False
 
     # ---- subclass API (same names as the reference) -------------------------------------------------------
     def _transform_dim_multiplier(self):
@@ -296,12 +308,27 @@ class PiecewiseRationalQuadraticCouplingTransform(PiecewiseCouplingTransform):
             raise RuntimeError("{} tails are not implemented.".format(self.tails))
         return self.num_bins <= 64
 
-    def _native_epilogue(self, x, params, t_cols, id_cols, out, lad, flags, inverse):
+    def _spline_desc(self):
         if self.min_bin_width * self.num_bins > 1.0:
             raise ValueError("Minimal bin width too large for the number of bins")
         if self.min_bin_height * self.num_bins > 1.0:
             raise ValueError("Minimal bin height too large for the number of bins")
         divisor = self._softmax_divisor()
-        desc = N.spline_desc(self.num_bins, self.tails, self.tail_bound, 0.0, 1.0, 0.0, 1.0, self.min_bin_width,
+        return N.spline_desc(self.num_bins, self.tails, self.tail_bound, 0.0, 1.0, 0.0, 1.0, self.min_bin_width,
                              self.min_bin_height, self.min_derivative, False, 1.0 if divisor is None else divisor)
-        K.rqs_rows(desc, inverse, x, params, t_cols, id_cols, lad, flags, out=out)
+
+    def _native_epilogue(self, x, params, t_cols, id_cols, out, lad, flags, inverse):
+        K.rqs_rows(self._spline_desc(), inverse, x, params, t_cols, id_cols, lad, flags, out=out)
+
+    def _fused_final_ready(self, chain):
+        weight, bias, relu_in, relu_out, residual = chain[-1]
+        hidden = weight.shape[1]
+        return (config.fuse_coupling and bias is not None and not relu_out and residual is None
+                and K.rq_coupling_final_supported(self.num_bins, self.tails, hidden, hidden))
+
+    def _fused_final(self, chain, state, x, t_cols, out, lad, flags, inverse):
+        weight, bias = chain[-1][0], chain[-1][1]
+        m = self._transform_dim_multiplier()
+        mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
+        wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.num_transform_features, m, mp)
+        K.rq_coupling_final(self._spline_desc(), inverse, state.pair, wp_pair, bias_packed, x, t_cols, out, lad, flags)
