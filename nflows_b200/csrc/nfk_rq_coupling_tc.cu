@@ -167,16 +167,21 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HC;
 #pragma unroll
-                    for (int c = 0; c < HC; c += 8) {
-                        uint32_t raw[8];
-                        tmem_ld8(taddr + c, raw);
+                    for (int c = 0; c < HC; c += 24) {                 // 3 loads in flight per wait (HC is a multiple of 8)
+                        uint32_t raw[3][8];
+#pragma unroll
+                        for (int u = 0; u < 3; ++u)
+                            if (c + 8 * u < HC) tmem_ld8(taddr + c + 8 * u, raw[u]);
                         tmem_ld_wait();
-                        if (ks == 0) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) sum[c + i] = __uint_as_float(raw[i]);
-                        } else {
+                        for (int u = 0; u < 3; ++u) {
+                            if (c + 8 * u < HC) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) sum[c + i] = __fadd_rn(sum[c + i], __uint_as_float(raw[i]));
+                                for (int i = 0; i < 8; ++i) {
+                                    const float v = __uint_as_float(raw[u][i]);
+                                    sum[c + 8 * u + i] = (ks == 0) ? v : __fadd_rn(sum[c + 8 * u + i], v);
+                                }
+                            }
                         }
                     }
                     tc_fence_before();
@@ -188,8 +193,9 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 #pragma unroll
                 for (int f = 0; f < FPT; ++f) {
                     const int j = j0 + f;
-                    if (row_ok && j < p.d_t) {
-                        const float* bj = p.bias + (int64_t)j * MP;
+                    const bool live = row_ok && j < p.d_t;
+                    {
+                        const float* bj = p.bias + (int64_t)(live ? j : 0) * MP;
                         float w[NB], h[NB], d[NB + 1];
 #pragma unroll
                         for (int k = 0; k < NB; ++k) {
@@ -206,9 +212,13 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                             for (int k = 0; k <= NB; ++k) d[k] = sum[f * MP + 2 * NB + k] + __ldg(bj + 2 * NB + k);
                         }
                         float yy, ll;
-                        rqs_eval<NB>(p.sp, p.inverse != 0, xin[f], w, h, d, yy, ll, flag);
-                        p.y[row * p.ldy + col[f]] = yy;
-                        lad_row += ll;
+                        int fl = 0;
+                        rqs_eval<NB>(p.sp, p.inverse != 0, xin[f], w, h, d, yy, ll, fl);
+                        if (live) {
+                            p.y[row * p.ldy + col[f]] = yy;
+                            lad_row += ll;
+                            flag |= fl;
+                        }
                     }
                 }
                 __syncwarp();

@@ -39,46 +39,53 @@ __device__ __forceinline__ float softplus_torch(float x, float beta, float inv_b
     return xb > 20.0f ? x : log1pf(expf(xb)) * inv_beta;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // KMAX: compile-time bound on the number of bins (register arrays); p.num_bins <= KMAX.
 // uw/uh: K raw values (before the 1/sqrt(H) pre-scale); ud: K+1 raw derivative logits (already padded with
 // edge_ud for linear tails).  Returns y and log|dy/dx|; sets flag bits for domain / discriminant violations.
+//
+// Written branch-free (outside-the-tails elements are evaluated on a clamped input and discarded by a select) so
+// that several elements of one thread can be interleaved by the scheduler, and with the cheap forms that keep the
+// result inside the fp32 round-off of the reference: softmax as ex2((u - max) * log2e/sqrt(H)) (MUFU, rel. error
+// <= 2^-22) normalised by ONE reciprocal per softmax instead of K divisions; the bin ratio, theta and the rational
+// function keep IEEE divisions, logf/log1pf/expf of the two derivatives and of the log-determinant stay accurate.
 template <int KMAX>
-__device__ __forceinline__ void rqs_eval(const SplineParams& p, bool inverse, float x, const float (&uw)[KMAX],
+__device__ __forceinline__ void rqs_eval(const SplineParams& p, bool inverse, float x_in, const float (&uw)[KMAX],
                                          const float (&uh)[KMAX], const float (&ud)[KMAX + 1], float& y, float& lad,
                                          int& flag) {
     const int K = p.num_bins;
-    if (p.linear_tails) {
-        bool inside = (x >= p.left) && (x <= p.right);   // NaN -> outside -> identity, lad 0 (reference :26-39)
-        if (!inside) { y = x; lad = 0.0f; return; }
-    } else if (!(x >= p.left && x <= p.right)) {
-        flag |= 1;                                        // reference raises InputOutsideDomain (:81-82)
-        x = fminf(fmaxf(x, p.left), p.right);
-    }
+    const bool inside = (x_in >= p.left) && (x_in <= p.right);   // NaN -> outside (reference :26-39)
+    if (!p.linear_tails && !inside) flag |= 1;                   // reference raises InputOutsideDomain (:81-82)
+    const float x = inside ? x_in : (x_in > p.right ? p.right : p.left);
 
     float ew[KMAX], eh[KMAX];
     float mw = -INFINITY, mh = -INFINITY;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-            ew[k] = uw[k] * p.pre_scale;
-            eh[k] = uh[k] * p.pre_scale;
-            mw = fmaxf(mw, ew[k]);
-            mh = fmaxf(mh, eh[k]);
+            mw = fmaxf(mw, uw[k]);
+            mh = fmaxf(mh, uh[k]);
         }
     }
+    const float c2 = p.pre_scale * 1.4426950408889634f;          // log2(e) / sqrt(H)
     float sw = 0.0f, sh = 0.0f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-            ew[k] = expf(ew[k] - mw);
-            eh[k] = expf(eh[k] - mh);
+            ew[k] = ex2_approx((uw[k] - mw) * c2);
+            eh[k] = ex2_approx((uh[k] - mh) * c2);
             sw += ew[k];
             sh += eh[k];
         }
     }
+    const float rw = p.mix_w / sw, rh = p.mix_h / sh;
 
     // running prefix sums -> knots; select the bin on the fly
-    const float q = x;
     float cum_w = 0.0f, cum_h = 0.0f;
     float kw_lo = p.left, kh_lo = p.bottom;              // knot k
     float b_cw = p.left, b_ch = p.bottom, b_w = 1.0f, b_h = 1.0f;
@@ -86,18 +93,16 @@ __device__ __forceinline__ void rqs_eval(const SplineParams& p, bool inverse, fl
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         if (k < K) {
-            float fw = p.min_w + p.mix_w * (ew[k] / sw);
-            float fh = p.min_h + p.mix_h * (eh[k] / sh);
-            cum_w += fw;
-            cum_h += fh;
-            float kw_hi = (k == K - 1) ? p.right : p.span_w * cum_w + p.left;   // knot k+1
-            float kh_hi = (k == K - 1) ? p.top : p.span_h * cum_h + p.bottom;
-            bool take = (k == 0) || (q >= (inverse ? kh_lo : kw_lo));
-            if (take) {
-                bin = k;
-                b_cw = kw_lo; b_ch = kh_lo;
-                b_w = kw_hi - kw_lo; b_h = kh_hi - kh_lo;
-            }
+            cum_w += fmaf(ew[k], rw, p.min_w);
+            cum_h += fmaf(eh[k], rh, p.min_h);
+            const float kw_hi = (k == K - 1) ? p.right : fmaf(p.span_w, cum_w, p.left);   // knot k+1
+            const float kh_hi = (k == K - 1) ? p.top : fmaf(p.span_h, cum_h, p.bottom);
+            const bool take = (k == 0) || (x >= (inverse ? kh_lo : kw_lo));
+            bin = take ? k : bin;
+            b_cw = take ? kw_lo : b_cw;
+            b_ch = take ? kh_lo : b_ch;
+            b_w = take ? kw_hi - kw_lo : b_w;
+            b_h = take ? kh_hi - kh_lo : b_h;
             kw_lo = kw_hi; kh_lo = kh_hi;
         }
     }
@@ -105,36 +110,39 @@ __device__ __forceinline__ void rqs_eval(const SplineParams& p, bool inverse, fl
     float ud0 = ud[0], ud1 = ud[1];
 #pragma unroll
     for (int k = 1; k < KMAX; ++k) {
-        if (k == bin) { ud0 = ud[k]; ud1 = ud[k + 1]; }
+        ud0 = (k == bin) ? ud[k] : ud0;
+        ud1 = (k == bin) ? ud[k + 1] : ud1;
     }
     const float d0 = p.min_d + softplus_torch(ud0, p.beta, p.inv_beta);
     const float d1 = p.min_d + softplus_torch(ud1, p.beta, p.inv_beta);
     const float delta = b_h / b_w;
     const float s = d0 + d1 - 2.0f * delta;
 
-    float theta;
+    float theta, ys;
     if (inverse) {
-        float u = x - b_ch;
-        float a = u * s + b_h * (delta - d0);
-        float b = b_h * d0 - u * s;
-        float c = -delta * u;
-        float disc = b * b - 4.0f * a * c;
+        const float u = x - b_ch;
+        const float a = u * s + b_h * (delta - d0);
+        const float b = b_h * d0 - u * s;
+        const float c = -delta * u;
+        const float disc = b * b - 4.0f * a * c;
         if (!(disc >= 0.0f)) flag |= 2;                   // reference: assert (discriminant >= 0).all() (:142)
         theta = (2.0f * c) / (-b - sqrtf(disc));
-        y = theta * b_w + b_cw;
+        ys = theta * b_w + b_cw;
     } else {
         theta = (x - b_cw) / b_w;
     }
     const float t1mt = theta * (1.0f - theta);
     const float den = delta + s * t1mt;
     if (!inverse) {
-        float num = b_h * (delta * (theta * theta) + d0 * t1mt);
-        y = b_ch + num / den;
+        const float num = b_h * (delta * (theta * theta) + d0 * t1mt);
+        ys = b_ch + num / den;
     }
     const float omt = 1.0f - theta;
     const float dnum = (delta * delta) * (d1 * (theta * theta) + 2.0f * delta * t1mt + d0 * (omt * omt));
     const float l = logf(dnum) - 2.0f * logf(den);
-    lad = inverse ? -l : l;
+    const bool identity = p.linear_tails && !inside;
+    y = identity ? x_in : ys;
+    lad = identity ? 0.0f : (inverse ? -l : l);
 }
 
 }  // namespace nfk

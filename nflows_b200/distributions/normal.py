@@ -29,7 +29,7 @@ class StandardNormal(Distribution):
         Flow._log_prob finishes (flows/base.py:49 in the reference adds the two afterwards)."""
         self._check_shape(inputs)
         if K.native_ok(inputs) and (logabsdet is None or K.native_ok(logabsdet)):
-            flat = inputs.reshape(inputs.shape[0], -1)
+            flat = inputs.reshape(inputs.shape[0], int(np.prod(self._shape)))
             if flat.stride(-1) != 1:
                 flat = flat.contiguous()
             return K.std_normal_log_prob(flat, self._log_z_host, logabsdet)
