@@ -102,6 +102,38 @@ def cpu_oracle_rate(flow, budget_s=12.0, chunk=2048, max_rows=1 << 15):
     return rows / dt, rows, torch.get_num_threads()
 
 
+def spline_hbm_roofline(dev, peaks, rows=1 << 20, d_t=32, bins=8, iters=10):
+    """The HBM-bound spline segment (BASELINE configs[1] shape): conditioner output [rows, d_t*(3K-1)] resident in HBM ->
+    nfk_rqs_rows.  Algorithmic bytes = 4*(M+2) per transformed element + 4 per identity element copied (read+write)."""
+    from nflows_b200 import _native as N
+    from nflows_b200 import kernels as K
+    m = 3 * bins - 1
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(rows, 2 * d_t, device=dev, generator=g)
+    params = torch.randn(rows, d_t * m, device=dev, generator=g)
+    t_cols = torch.arange(0, 2 * d_t, 2, device=dev, dtype=torch.int32)
+    id_cols = torch.arange(1, 2 * d_t, 2, device=dev, dtype=torch.int32)
+    lad = torch.zeros(rows, device=dev)
+    y = torch.empty_like(x)
+    flags = K.new_flags(dev)
+    desc = N.spline_desc(bins, "linear", 3.0, 0, 1, 0, 1, 1e-3, 1e-3, 1e-3, False, 128.0 ** 0.5)
+    for _ in range(3):
+        K.rqs_rows(desc, False, x, params, t_cols, id_cols, lad, flags, out=y)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        K.rqs_rows(desc, False, x, params, t_cols, id_cols, lad, flags, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = rows * (d_t * (4 * (m + 2)) + d_t * 8 + 8)
+    achieved = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "rqs_rows_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "avg_launch_ms": ms,
+            "workload": "rows=2^20 d_t=32 K=8 params in HBM (3.2 GB > L2)", "peak_kind": "copy bandwidth, %s" % peaks["source"]}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; the Python reference itself cannot travel to the GPU box)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -192,10 +224,15 @@ def run_native(args):
         fence()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
+        from nflows_b200 import sharding
+        lp_dev = torch.empty(rows, device=dev)
         for _ in range(e2e_steps):
-            xd = host_x.to(dev, non_blocking=True)
-            o = step(xd)
-            host_out.copy_(o, non_blocking=True)
+            sharding.log_prob_streamed(flow, host_x, dev, chunk_rows=1 << 18, out=lp_dev)   # H2D overlapped with the kernels
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, lp_dev)
+                host_out.copy_(gathered, non_blocking=True)
+            else:
+                host_out.copy_(lp_dev, non_blocking=True)
         f1.record()
         fence()
         ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
@@ -236,10 +273,18 @@ def run_native(args):
         flops = FLOP_FINAL_PER_ROW * rows_k
         achieved = flops / (tms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath))
+            if t.get("kernel") == tag and t.get("rows_per_launch") == rows_k // count:
+                traffic = t["dram_bytes_per_launch"]
         result["roofline"] = {"kernel": tag, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                              "frac": achieved / peak, "traffic": None, "launches": count,
+                              "frac": achieved / peak, "traffic": traffic, "launches": count,
                               "avg_launch_ms": tms / count, "share_of_step": tms / ms_total,
                               "peak_kind": "bf16 dense sustained, %s" % peaks["source"]}
+    if not args.no_spline_roofline:
+        result["roofline_spline"] = spline_hbm_roofline(dev, peaks)
     # ---- CPU baseline (oracle port) on this box's host cores ---------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
         rate, sample_rows, threads = cpu_oracle_rate(flow.cpu(), budget_s=args.ref_budget, max_rows=args.ref_rows)
@@ -260,6 +305,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per reference step")
     ap.add_argument("--ref-rows", type=int, default=1 << 15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spline-roofline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,90 @@
+"""Batch sharding of Flow.log_prob / Flow.sample across the GPUs of one box, and host-streamed evaluation.
+
+Every sample of the path is independent (no batch statistics in eval mode), so the path shards with NO data-path
+collective: one process per GPU (torchrun), a full replica of the weights per rank, rank r owns rows
+[lo_r, hi_r).  The only exchange is the optional all-gather of the per-sample log-probs at the end (4 bytes per row,
+NCCL over NVLink; latency-bound).  The reference has no distributed code at all."""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_rows, world_size, rank):
+    """Contiguous near-equal shards: the first n_rows % world_size ranks get one extra row."""
+    base, extra = divmod(int(n_rows), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def gather_rows(local, n_rows_total, group=None):
+    """All-gather per-row results of ragged contiguous shards back into global row order on every rank."""
+    world, rank = _world(group)
+    if world == 1:
+        return local
+    sizes = [shard_bounds(n_rows_total, world, r) for r in range(world)]
+    counts = [hi - lo for lo, hi in sizes]
+    if len(set(counts)) == 1:
+        out = local.new_empty((n_rows_total,) + tuple(local.shape[1:]))
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    width = max(counts)
+    padded = local.new_zeros((width,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+@torch.no_grad()
+def log_prob_sharded(flow, inputs, context=None, group=None, gather=True):
+    """`inputs` (and `context`) are the FULL batch, replicated or addressable on every rank; each rank evaluates its
+    shard with its own replica of `flow` and (optionally) all ranks receive the full [n_rows] result."""
+    world, rank = _world(group)
+    lo, hi = shard_bounds(inputs.shape[0], world, rank)
+    local = flow.log_prob(inputs[lo:hi], None if context is None else context[lo:hi])
+    return gather_rows(local, inputs.shape[0], group) if gather else local
+
+
+@torch.no_grad()
+def log_prob_streamed(flow, host_inputs, device, chunk_rows=1 << 17, out=None):
+    """Flow.log_prob of a (pinned) HOST tensor: chunks are copied on a side stream while the previous chunk is being
+    evaluated, so the host->device transfer hides behind the kernels.  Returns the [n_rows] result on `device`."""
+    n = host_inputs.shape[0]
+    result = out if out is not None else torch.empty(n, dtype=torch.float32, device=device)
+    if n == 0:
+        return result
+    copy_stream = torch.cuda.Stream(device=device)
+    compute = torch.cuda.current_stream(device)
+    buffers, ready = [None, None], [None, None]
+
+    def stage(i, lo):
+        hi = min(n, lo + chunk_rows)
+        with torch.cuda.stream(copy_stream):
+            if buffers[i] is not None:
+                copy_stream.wait_event(ready[i])          # previous consumer of this buffer has finished
+            buffers[i] = host_inputs[lo:hi].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return hi, ev
+
+    starts = list(range(0, n, chunk_rows))
+    hi, ev = stage(0, starts[0])
+    pending = (0, starts[0], hi, ev)
+    for k in range(len(starts)):
+        i, lo, hi, ev = pending
+        if k + 1 < len(starts):
+            j = (k + 1) & 1
+            nhi, nev = stage(j, starts[k + 1])
+            pending = (j, starts[k + 1], nhi, nev)
+        compute.wait_event(ev)
+        buffers[i].record_stream(compute)
+        result[lo:hi] = flow.log_prob(buffers[i])
+        done = torch.cuda.Event()
+        done.record(compute)
+        ready[i] = done
+    return result
