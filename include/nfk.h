@@ -109,7 +109,8 @@ int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_c
  *   a_hi/a_lo  : split pair of the last hidden activation [n_rows, hidden_features]
  *   wp_hi/wp_lo: split pair of the PACKED final weight [d_t * MP, hidden_features]: row j*MP + k = reference row j*M + k
  *                for k < M, zero rows for M <= k < MP, MP = nfk_rq_coupling_final_padded_params(num_bins, tails)
- *   bias_packed: [d_t * MP] packed the same way
+ *   bias_packed: packed the same way and zero-padded to a whole number of tiles: [ceil(d_t / (2*FPT)) * 2*FPT * MP] with
+ *                FPT = 128 / MP (the kernel adds it per tile column)
  * Writes y[n, t_cols[j]] for every transformed feature (the caller copies the identity columns, e.g. with the
  * copy_dst of nfk_split_tf32) and adds the row's log|det| to lad_accum.  nfk_rq_coupling_final_supported says whether an
  * instance exists for (num_bins, tails, hidden_features, lda); otherwise use nfk_linear* + nfk_rqs_rows. */

@@ -115,8 +115,10 @@ def pack_final_spline(weight, bias, d_t, m, mp):
         k = w.shape[1]
         wp = w.new_zeros(d_t, mp, k)
         wp[:, :m, :] = w.reshape(d_t, m, k)
-        bp = b.new_zeros(d_t, mp)
-        bp[:, :m] = b.reshape(d_t, m)
+        fpt = 128 // mp                                   # features per thread in the fused kernel (FusedCfg::FPT)
+        tiles = -(-d_t // (2 * fpt))
+        bp = b.new_zeros(tiles * 2 * fpt, mp)             # padded to whole tiles: the kernel reads bias per tile column
+        bp[:d_t, :m] = b.reshape(d_t, m)
         hit = (sig, K.split_tf32(wp.reshape(d_t * mp, k)), bp.reshape(-1).contiguous(), weight)
         _PACK_CACHE[key] = hit
         if len(_PACK_CACHE) > 1024:
