@@ -23,7 +23,8 @@
 //                                tcgen05.ld of each partial sum -> 128 running sums per thread in registers; at the end of
 //                                a tile bias / relu / residual -> global stores of the fp32 result and/or the split pair
 //                                consumed by the next layer
-//   smem ring: 2 stages x (A_hi, A_lo, W_hi, W_lo) = 2 x 96 KB;  TMEM: 2 partial accumulators x 256 columns.
+//   smem ring: 4 stages x (A_hi, A_lo, W_hi, W_lo) of K = 16 = 4 x 48 KB (three loads in flight while one slab is
+//   consumed: the 2 x 96 KB ring of the first version was latency-bound);  TMEM: 2 partial accumulators x 256 columns.
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -288,7 +289,7 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int K, int64_t l
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return NFK_OK;

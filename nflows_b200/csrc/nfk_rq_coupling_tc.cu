@@ -182,6 +182,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (p.K + BK - 1) / BK;
+    const int num_groups = (num_k + DRAIN_SLABS - 1) / DRAIN_SLABS;     // partial sums per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -219,7 +220,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 }
             }
         } else if (warp == 1) {
-            // ================================================= MMA issuer (one thread): one partial sum per K-slab
+            // ================================================= MMA issuer (one thread): one partial sum per DRAIN_SLABS slabs
             if (lane == 0) {
                 const uint32_t idesc = make_idesc(BN);
                 int stage = 0; uint32_t phase = 0;
@@ -227,7 +228,9 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
                     for (int n = 0; n < p.num_n_tiles; ++n) {
                         for (int ks = 0; ks < num_k; ++ks) {
-                            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                            const bool group_start = (ks % DRAIN_SLABS) == 0;
+                            const bool group_end = (ks % DRAIN_SLABS) == DRAIN_SLABS - 1 || ks == num_k - 1;
+                            if (group_start) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                             mbar_wait(bar_full + 8 * stage, phase);
                             tc_fence_after();
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
@@ -237,7 +240,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 #pragma unroll
                             for (int kk = 0; kk < BK / 8; ++kk) {          // cross terms first (see nfk_linear_tc.cu)
                                 const uint64_t adv = (uint64_t)(kk * 2);
-                                umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, kk != 0);
+                                umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, !group_start || kk != 0);
                                 umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                             }
 #pragma unroll
@@ -246,9 +249,11 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                                 umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                             }
                             umma_commit(bar_empty + 8 * stage);
-                            umma_commit(bar_tfull + 8 * acc);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                            if (group_end) {
+                                umma_commit(bar_tfull + 8 * acc);
+                                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                            }
                         }
                     }
                 }
@@ -277,7 +282,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 }
                 const float* bias_tile = p.bias + (int64_t)n * BN + half * HC;     // packed bias of this thread's columns
                 float sum[HC];
-                for (int ks = 0; ks < num_k; ++ks) {
+                for (int ks = 0; ks < num_groups; ++ks) {
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HC;

@@ -10,10 +10,10 @@ namespace tc {
 
 constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int BN_MAX = 256;        // columns per tile (runtime BN <= BN_MAX, multiple of 16)
-constexpr int BK = 32;             // fp32 elements per K-slab = one 128-byte swizzle row
-constexpr int STAGES = 2;
+constexpr int BK = 16;             // fp32 elements per K-slab = one 64-byte swizzle row (SWIZZLE_64B)
+constexpr int STAGES = 4;          // 4 x 48 KB slabs: 3 TMA loads in flight while one slab is consumed
 constexpr int THREADS = 384;        // warpgroup 0: TMA + MMA warps (2 idle); warpgroups 1-2: accumulate/epilogue
-constexpr int DRAIN_SLABS = 1;       // K-slabs accumulated inside the tensor core before a drain (K = 32: 12 MMAs)
+constexpr int DRAIN_SLABS = 2;       // K-slabs accumulated inside the tensor core before a drain (K = 32: 12 MMAs)
 constexpr int HALF = BN_MAX / 2;     // columns per epilogue warp
 constexpr int A_BYTES = BM * BK * 4;             // 16 KB
 constexpr int B_BYTES = BN_MAX * BK * 4;         // 32 KB
@@ -97,11 +97,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x 128 B = 1024 B)
-// | [46,48) version=1 (sm_100) | [61,64) layout 2 = SWIZZLE_128B
+// K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x row bytes)
+// | [46,48) version=1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B (128-byte rows), 4 = SWIZZLE_64B (64-byte rows)
+constexpr int ROW_BYTES = BK * 4;
+static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "K-slab rows must be 64 or 128 bytes");
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * ROW_BYTES) >> 4) << 32) | (1ull << 46) |
+           ((uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61);
 }
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int bn) {

@@ -34,12 +34,29 @@ def searchsorted(bin_locations, inputs, eps=1e-6):
     return torch.sum(inputs[..., None] >= bin_locations, dim=-1) - 1
 
 
+#: ATen's CPU cumsum accumulates float inputs in DOUBLE (acc_type<float, false>), its CUDA cumsum in float.  The
+#: reference run on a GPU therefore has less accurate knots than the CPU goldens; set this to emulate the CUDA
+#: semantics (sequential float accumulation) when calibrating tolerances for sharp-bin stress vectors.
+F32_CUMSUM = False
+
+
+def _cumsum(frac):
+    if not F32_CUMSUM or frac.dtype != torch.float32:
+        return torch.cumsum(frac, dim=-1)
+    out = torch.empty_like(frac)
+    run = torch.zeros_like(frac[..., 0])
+    for i in range(frac.shape[-1]):
+        run = run + frac[..., i]
+        out[..., i] = run
+    return out
+
+
 def _knots(unnormalized, lo, hi, min_size):
     """transforms/splines/rational_quadratic.py:91-98 (widths) and :106-113 (heights)."""
     k = unnormalized.shape[-1]
     frac = F.softmax(unnormalized, dim=-1)
     frac = min_size + (1 - min_size * k) * frac
-    cum = torch.cumsum(frac, dim=-1)
+    cum = _cumsum(frac)
     cum = F.pad(cum, pad=(1, 0), mode="constant", value=0.0)
     cum = (hi - lo) * cum + lo
     cum[..., 0] = lo
