@@ -10,8 +10,15 @@
 //   * only the two derivatives the bin needs go through softplus (threshold 20, like F.softplus);
 //   * forward: theta=(x-cw)/w ...; inverse: root = 2c / (-b - sqrt(b^2-4ac)) (:132-181).
 #pragma once
-#include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define NFK_HD __device__ __forceinline__
+#else
+#define NFK_HD static inline      // host build: oracle/rqs_host.cpp evaluates the SAME source on the CPU
+#endif
 
 #include "../../include/nfk.h"
 
@@ -33,16 +40,20 @@ struct SplineParams {        // derived on the host in double precision, rounded
 // host: derive the fp32 constants from the descriptor (nfk_spline.cu)
 int make_spline_params(const NfkSplineDesc* d, SplineParams* p);
 
-__device__ __forceinline__ float softplus_torch(float x, float beta, float inv_beta) {
+NFK_HD float softplus_torch(float x, float beta, float inv_beta) {
     // F.softplus(x, beta, threshold=20): x*beta > 20 ? x : log1p(exp(x*beta))/beta
     float xb = x * beta;
     return xb > 20.0f ? x : log1pf(expf(xb)) * inv_beta;
 }
 
-__device__ __forceinline__ float ex2_approx(float x) {
+NFK_HD float ex2_approx(float x) {
+#ifdef __CUDA_ARCH__
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#else
+    return exp2f(x);
+#endif
 }
 
 // KMAX: compile-time bound on the number of bins (register arrays); p.num_bins <= KMAX.
@@ -55,7 +66,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // <= 2^-22) normalised by ONE reciprocal per softmax instead of K divisions; the bin ratio, theta and the rational
 // function keep IEEE divisions, logf/log1pf/expf of the two derivatives and of the log-determinant stay accurate.
 template <int KMAX>
-__device__ __forceinline__ void rqs_eval(const SplineParams& p, bool inverse, float x_in, const float (&uw)[KMAX],
+NFK_HD void rqs_eval(const SplineParams& p, bool inverse, float x_in, const float (&uw)[KMAX],
                                          const float (&uh)[KMAX], const float (&ud)[KMAX + 1], float& y, float& lad,
                                          int& flag) {
     const int K = p.num_bins;

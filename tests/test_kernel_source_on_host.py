@@ -1,0 +1,69 @@
+"""The per-element spline source of the CUDA kernels (nflows_b200/csrc/rq_spline.cuh) compiled for the HOST
+(oracle/rqs_host.cpp) and checked against the reference's golden vectors and the fp64 oracle -- kernel numerics
+without a GPU.  (The GPU run of the same source is checked in test_native_parity.py.)"""
+import ctypes
+import os
+import subprocess
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from nflows_b200._native import spline_desc
+from oracle import flow_oracle as O
+
+
+@pytest.fixture(scope="module")
+def host_lib():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    return ctypes.CDLL(os.path.join(ROOT, "oracle", "_build", "librqs_host.so"))
+
+
+def run(lib, desc, inverse, x, uw, uh, ud):
+    x, uw, uh, ud = (t.contiguous().float() for t in (x, uw, uh, ud))
+    y, lad, flag = torch.empty_like(x), torch.empty_like(x), ctypes.c_int(0)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.rqs_host_eval(ctypes.byref(desc), int(inverse), p(x), p(uw), p(uh), p(ud), ctypes.c_longlong(x.numel()), p(y),
+                           p(lad), ctypes.byref(flag))
+    assert rc == 0
+    return y, lad, flag.value
+
+
+def errs(a, b):
+    a, b = a.double(), b.double()
+    nan = torch.isnan(a) & torch.isnan(b)
+    e = (a - b).abs() / torch.maximum(torch.maximum(a.abs(), b.abs()), torch.ones_like(a))
+    return torch.where(nan, torch.zeros_like(e), e).flatten().sort().values
+
+
+def test_kernel_source_matches_reference_distribution(host_lib):
+    g = load_golden("spline")
+    cases = [("tails", g["x_tails"], g["ud_tails"], spline_desc(8, "linear", 3.0, 0, 1, 0, 1, 1e-3, 1e-3, 1e-3)),
+             ("constrained", g["x_constrained"], g["ud_constrained"], spline_desc(8, None, 1.0, 0, 1, 0, 1, 1e-3, 1e-3, 1e-3))]
+    for name, x, ud, desc in cases:
+        for inv in (False, True):
+            y, lad, _ = run(host_lib, desc, inv, x, g["uw"], g["uh"], ud)
+            if name == "tails":
+                ty, tl = O.rq_spline_unconstrained(x.double(), g["uw"].double(), g["uh"].double(), ud.double(), inverse=inv,
+                                                   tail_bound=3.0)
+            else:
+                ty, tl = O.rq_spline(x.double(), g["uw"].double(), g["uh"].double(), ud.double(), inverse=inv)
+            wy, wl = g["%s_inv%d" % (name, inv)]
+            for got, ref, truth in ((y, wy, ty), (lad, wl, tl)):
+                e, r = errs(got, truth), errs(ref, truth)
+                n = len(e)
+                for q in (0.5, 0.99, 0.999):
+                    i = min(n - 1, int(q * n))
+                    assert e[i] <= 2 * r[i] + 1e-5, (name, inv, q, float(e[i]), float(r[i]))
+                assert e[-1] <= 30 * r[-1] + 1e-5
+
+
+def test_kernel_source_identity_and_domain_flag(host_lib):
+    k = 10
+    x = torch.rand(500)
+    z, zd = torch.zeros(500, k), torch.zeros(500, k + 1)
+    desc = spline_desc(k, None, 1.0, 0, 1, 0, 1, 1e-3, 1e-3, 1e-3, enable_identity_init=True)
+    y, lad, flag = run(host_lib, desc, False, x, z, z, zd)
+    assert float((y - x).abs().max()) <= 1e-6 and float(lad.abs().max()) <= 1e-6 and flag == 0
+    _, _, flag = run(host_lib, desc, False, x + 1.0, z, z, zd)
+    assert flag & 1
