@@ -106,24 +106,33 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 for (int g = 0; g < num_groups; ++g) {
+                    // one partial sum = DRAIN_SLABS resident K-slabs; every small cross term (lo*hi, hi*lo) is issued before
+                    // the first main product, so only the main MMAs round at full magnitude
+                    const int slabs = min(DRAIN_SLABS, num_k - g * DRAIN_SLABS);
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);      // epilogue has drained this partial accumulator
+                    int st = stage; uint32_t ph = phase;
+                    for (int j = 0; j < slabs; ++j) {
+                        mbar_wait(bar_full + 8 * st, ph);                  // TMA bytes have landed
+                        if (++st == STAGES) { st = 0; ph ^= 1; }
+                    }
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-                    const int ks_end = min(num_k, (g + 1) * DRAIN_SLABS);
-                    for (int ks = g * DRAIN_SLABS; ks < ks_end; ++ks) {
-                        mbar_wait(bar_full + 8 * stage, phase);            // TMA bytes have landed
-                        tc_fence_after();
-                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    st = stage;
+                    for (int j = 0; j < slabs; ++j) {
+                        const uint32_t sa = smem_base + st * STAGE_BYTES;
                         const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
                         const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
-                        // UMMA K = 8 tf32 = 32 bytes = +2 in descriptor units.  The small cross terms go first, while the
-                        // accumulator is still ~2^-11 of its final size, so only the BK/8 main products round at full size.
 #pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk) {
+                        for (int kk = 0; kk < BK / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes = +2 in descriptor units
                             const uint64_t adv = (uint64_t)(kk * 2);
-                            umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (ks != g * DRAIN_SLABS) || kk != 0);
+                            umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j | kk) != 0);
                             umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                         }
+                        if (++st == STAGES) st = 0;
+                    }
+                    for (int j = 0; j < slabs; ++j) {
+                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                        const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
 #pragma unroll
                         for (int kk = 0; kk < BK / 8; ++kk) {
                             const uint64_t adv = (uint64_t)(kk * 2);
@@ -166,7 +175,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         for (int j = 0; j < 16; ++j) sum[c + j] = __uint_as_float(raw[j]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) sum[c + j] = __fadd_rn(sum[c + j], __uint_as_float(raw[j]));
+                        for (int j = 0; j < 16; j += 2) {                  // packed fp32x2 round-to-nearest adds (FADD2)
+                            const float2 r2 = __fadd2_rn(make_float2(sum[c + j], sum[c + j + 1]),
+                                                         make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])));
+                            sum[c + j] = r2.x;
+                            sum[c + j + 1] = r2.y;
+                        }
                     }
                 }
                 tc_fence_before();

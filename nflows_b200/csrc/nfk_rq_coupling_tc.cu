@@ -227,33 +227,44 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 int acc = 0; uint32_t acc_phase = 0;
                 for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
                     for (int n = 0; n < p.num_n_tiles; ++n) {
-                        for (int ks = 0; ks < num_k; ++ks) {
-                            const bool group_start = (ks % DRAIN_SLABS) == 0;
-                            const bool group_end = (ks % DRAIN_SLABS) == DRAIN_SLABS - 1 || ks == num_k - 1;
-                            if (group_start) mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-                            mbar_wait(bar_full + 8 * stage, phase);
+                        for (int g = 0; g < num_groups; ++g) {
+                            // one partial sum = DRAIN_SLABS resident K-slabs; every small cross term (lo*hi, hi*lo) is
+                            // issued before the first main product, so only the main MMAs round at full magnitude
+                            const int slabs = min(DRAIN_SLABS, num_k - g * DRAIN_SLABS);
+                            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                            int st = stage; uint32_t ph = phase;
+                            for (int j = 0; j < slabs; ++j) {
+                                mbar_wait(bar_full + 8 * st, ph);
+                                if (++st == STAGES) { st = 0; ph ^= 1; }
+                            }
                             tc_fence_after();
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-                            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
-                            const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+                            st = stage;
+                            for (int j = 0; j < slabs; ++j) {
+                                const uint32_t sa = smem_base + st * STAGE_BYTES;
+                                const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
+                                const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 8; ++kk) {          // cross terms first (see nfk_linear_tc.cu)
-                                const uint64_t adv = (uint64_t)(kk * 2);
-                                umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, !group_start || kk != 0);
-                                umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                                for (int kk = 0; kk < BK / 8; ++kk) {
+                                    const uint64_t adv = (uint64_t)(kk * 2);
+                                    umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j | kk) != 0);
+                                    umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                                }
+                                if (++st == STAGES) st = 0;
                             }
+                            for (int j = 0; j < slabs; ++j) {
+                                const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                                const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 8; ++kk) {
-                                const uint64_t adv = (uint64_t)(kk * 2);
-                                umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                                for (int kk = 0; kk < BK / 8; ++kk) {
+                                    const uint64_t adv = (uint64_t)(kk * 2);
+                                    umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                                }
+                                umma_commit(bar_empty + 8 * stage);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
                             }
-                            umma_commit(bar_empty + 8 * stage);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            if (group_end) {
-                                umma_commit(bar_tfull + 8 * acc);
-                                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                            }
+                            umma_commit(bar_tfull + 8 * acc);
+                            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         }
                     }
                 }
@@ -286,22 +297,42 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HC;
+                    if (ks == 0) {
+                        // first partial of the tile: running sum = bias + partial (bias_packed is padded to whole tiles)
 #pragma unroll
-                    for (int c = 0; c < HC; c += 24) {                 // 3 loads in flight per wait (HC is a multiple of 8)
-                        uint32_t raw[3][8];
+                        for (int c = 0; c < HC; c += 24) {             // 3 TMEM loads in flight per wait
+                            uint32_t raw[3][8];
 #pragma unroll
-                        for (int u = 0; u < 3; ++u)
-                            if (c + 8 * u < HC) tmem_ld8(taddr + c + 8 * u, raw[u]);
-                        tmem_ld_wait();
+                            for (int u = 0; u < 3; ++u)
+                                if (c + 8 * u < HC) tmem_ld8(taddr + c + 8 * u, raw[u]);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int u = 0; u < 3; ++u) {
-                            if (c + 8 * u < HC) {
+                            for (int u = 0; u < 3; ++u)
+                                if (c + 8 * u < HC) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float v = __uint_as_float(raw[u][i]);
-                                    sum[c + 8 * u + i] = __fadd_rn(ks == 0 ? __ldg(bias_tile + c + 8 * u + i) : sum[c + 8 * u + i], v);
+                                    for (int i = 0; i < 8; ++i)
+                                        sum[c + 8 * u + i] = __fadd_rn(__ldg(bias_tile + c + 8 * u + i), __uint_as_float(raw[u][i]));
                                 }
-                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < HC; c += 24) {
+                            uint32_t raw[3][8];
+#pragma unroll
+                            for (int u = 0; u < 3; ++u)
+                                if (c + 8 * u < HC) tmem_ld8(taddr + c + 8 * u, raw[u]);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int u = 0; u < 3; ++u)
+                                if (c + 8 * u < HC) {
+#pragma unroll
+                                    for (int i = 0; i < 8; i += 2) {       // packed fp32x2 round-to-nearest adds (FADD2)
+                                        const float2 r2 = __fadd2_rn(make_float2(sum[c + 8 * u + i], sum[c + 8 * u + i + 1]),
+                                                                     make_float2(__uint_as_float(raw[u][i]), __uint_as_float(raw[u][i + 1])));
+                                        sum[c + 8 * u + i] = r2.x;
+                                        sum[c + 8 * u + i + 1] = r2.y;
+                                    }
+                                }
                         }
                     }
                     tc_fence_before();
