@@ -11,6 +11,8 @@
 //     of its row in registers (K = 8 bins, linear tails: MP = 24, FPT = 5, BN = 240);
 //   * a CTA walks the N-tiles of one 128-row block consecutively, so every thread keeps the running log|det| of its row
 //     in a register and the row is finished (y written, lad_accum updated, deterministically) when the CTA moves on.
+#include <stdlib.h>
+
 #include "rq_spline.cuh"
 #include "tc_common.cuh"
 
@@ -163,7 +165,11 @@ __device__ __forceinline__ void rqs_eval_multi(const SplineParams& p, bool inver
     }
 }
 
-template <int NB, bool TAILS>
+// CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on neighbouring 128-row blocks and walk the same
+// sequence of weight tiles in lockstep: each loads HALF of every weight slab and multicasts it into both CTAs' shared
+// memory (cp.async.bulk.tensor ... .multicast::cluster), which halves the L2 -> SM weight stream -- the limiter of this
+// kernel (ncu: L2->SM 8.2 TB/s at 40 % tensor-pipe activity with CL = 1).
+template <int NB, bool TAILS, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -185,35 +191,48 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     const int num_groups = (num_k + DRAIN_SLABS - 1) / DRAIN_SLABS;     // partial sums per tile
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int first_block = blockIdx.x / CL, block_step = gridDim.x / CL;    // a "block" = CL neighbouring 128-row tiles
+    const int num_blocks = (p.num_m_tiles + CL - 1) / CL;
+    constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
         if (warp == 0) {
             // ================================================= TMA producer
             if (lane == 0) {
-                constexpr uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)BN * BK * 4u;
+                constexpr uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)BN * BK * 4u;   // bytes landing in THIS CTA's stage
+                constexpr int WROWS = BN / CL;                                             // weight rows this CTA fetches
                 int stage = 0; uint32_t phase = 0;
-                for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
+                for (int mb = first_block; mb < num_blocks; mb += block_step) {
+                    const int m = mb * CL + cta_rank;
                     for (int n = 0; n < p.num_n_tiles; ++n) {
                         for (int ks = 0; ks < num_k; ++ks) {
-                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);      // every CTA of the cluster has released the slot
                             const uint32_t full = bar_full + 8 * stage;
                             const uint32_t sa = smem_base + stage * STAGE_BYTES;
                             mbar_expect_tx(full, tx_bytes);
                             tma_load_2d(sa, &map_a_hi, full, ks * BK, m * BM);
                             tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m * BM);
-                            tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n * BN);
-                            tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n * BN);
+                            if (CL == 1) {
+                                tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n * BN);
+                                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n * BN);
+                            } else {
+                                const uint32_t off = (uint32_t)cta_rank * WROWS * ROW_BYTES;
+                                tma_load_2d_multicast(sa + 2 * A_BYTES + off, &map_w_hi, full, ks * BK, n * BN + cta_rank * WROWS, cl_mask);
+                                tma_load_2d_multicast(sa + 2 * A_BYTES + B_BYTES + off, &map_w_lo, full, ks * BK,
+                                                      n * BN + cta_rank * WROWS, cl_mask);
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -225,7 +244,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 const uint32_t idesc = make_idesc(BN);
                 int stage = 0; uint32_t phase = 0;
                 int acc = 0; uint32_t acc_phase = 0;
-                for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
+                for (int mb = first_block; mb < num_blocks; mb += block_step) {
                     for (int n = 0; n < p.num_n_tiles; ++n) {
                         for (int g = 0; g < num_groups; ++g) {
                             // one partial sum = DRAIN_SLABS resident K-slabs; every small cross term (lo*hi, hi*lo) is
@@ -260,7 +279,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                                     const uint64_t adv = (uint64_t)(kk * 2);
                                     umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                                 }
-                                umma_commit(bar_empty + 8 * stage);
+                                if (CL == 1) umma_commit(bar_empty + 8 * stage);
+                                else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // releases the slot in every CTA
                                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
                             }
                             umma_commit(bar_tfull + 8 * acc);
@@ -277,7 +297,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         const int half = (warp - 4) >> 2;         // which FPT features of the tile
         int acc = 0; uint32_t acc_phase = 0;
         int flag = 0;
-        for (int m = blockIdx.x; m < p.num_m_tiles; m += gridDim.x) {
+        for (int mb = first_block; mb < num_blocks; mb += block_step) {
+            const int m = mb * CL + cta_rank;
             const int64_t row = (int64_t)m * BM + q * 32 + lane;
             const bool row_ok = row < p.n_rows;
             float lad_row = 0.0f;
@@ -366,30 +387,58 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA exits while a peer may still signal its barriers
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int cluster_size() {
+    static int cl = 0;
+    if (!cl) {
+        const char* e = getenv("NFK_CLUSTER");
+        cl = (e && e[0] == '1') ? 1 : 2;
+    }
+    return cl;
+}
+
+template <int NB, bool TAILS, int CL>
+static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo, int64_t ldw,
+                           FusedParams& p, cudaStream_t st) {
+    using Cfg = FusedCfg<NB, TAILS>;
+    const int packed_rows = p.d_t * Cfg::MP;
+    CUtensorMap mw_hi, mw_lo;
+    int rc;
+    if ((rc = make_map(&mw_hi, w_hi, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
+    if ((rc = make_map(&mw_lo, w_lo, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
+    p.num_n_tiles = (p.d_t + 2 * Cfg::FPT - 1) / (2 * Cfg::FPT);
+    constexpr int smem = SMEM_BYTES + 512;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int blocks = (p.num_m_tiles + CL - 1) / CL;
+    const int max_clusters = sm_count() / CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CL * (blocks < max_clusters ? blocks : max_clusters)));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, CL>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(rq_coupling_final_kernel, cluster %d): %s", CL, cudaGetErrorString(e));
+    return check_launch("rq_coupling_final_kernel");
 }
 
 template <int NB, bool TAILS>
 static int launch_fused(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo, int64_t ldw,
                         FusedParams& p, cudaStream_t st) {
-    using Cfg = FusedCfg<NB, TAILS>;
-    const int packed_rows = p.d_t * Cfg::MP;
-    CUtensorMap mw_hi, mw_lo;
-    int rc;
-    if ((rc = make_map(&mw_hi, w_hi, packed_rows, p.K, ldw, Cfg::BN))) return rc;
-    if ((rc = make_map(&mw_lo, w_lo, packed_rows, p.K, ldw, Cfg::BN))) return rc;
-    p.num_n_tiles = (p.d_t + 2 * Cfg::FPT - 1) / (2 * Cfg::FPT);
-    constexpr int smem = SMEM_BYTES + 512;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
-        attr_set = true;
-    }
-    const int grid = p.num_m_tiles < sm_count() ? p.num_m_tiles : sm_count();
-    rq_coupling_final_kernel<NB, TAILS><<<grid, THREADS, smem, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
-    return check_launch("rq_coupling_final_kernel");
+    return cluster_size() == 2 ? launch_fused_cl<NB, TAILS, 2>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st)
+                               : launch_fused_cl<NB, TAILS, 1>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
 }
 
 }  // namespace tc
