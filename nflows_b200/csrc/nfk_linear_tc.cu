@@ -110,36 +110,39 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     // the first main product, so only the main MMAs round at full magnitude
                     const int slabs = min(DRAIN_SLABS, num_k - g * DRAIN_SLABS);
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);      // epilogue has drained this partial accumulator
-                    int st = stage; uint32_t ph = phase;
-                    for (int j = 0; j < slabs; ++j) {
-                        mbar_wait(bar_full + 8 * st, ph);                  // TMA bytes have landed
-                        if (++st == STAGES) { st = 0; ph ^= 1; }
-                    }
-                    tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-                    st = stage;
-                    for (int j = 0; j < slabs; ++j) {
-                        const uint32_t sa = smem_base + st * STAGE_BYTES;
-                        const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
-                        const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
-#pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes = +2 in descriptor units
-                            const uint64_t adv = (uint64_t)(kk * 2);
-                            umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j | kk) != 0);
-                            umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                    for (int j0 = 0; j0 < slabs; j0 += 2) {               // pairs of resident slabs: cross terms of both, then mains
+                        const int pair = min(2, slabs - j0);
+                        int st = stage; uint32_t ph = phase;
+                        for (int j = 0; j < pair; ++j) {
+                            mbar_wait(bar_full + 8 * st, ph);              // TMA bytes have landed
+                            if (++st == STAGES) { st = 0; ph ^= 1; }
                         }
-                        if (++st == STAGES) st = 0;
-                    }
-                    for (int j = 0; j < slabs; ++j) {
-                        const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                        const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
+                        tc_fence_after();
+                        st = stage;
+                        for (int j = 0; j < pair; ++j) {
+                            const uint32_t sa = smem_base + st * STAGE_BYTES;
+                            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
+                            const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                        for (int kk = 0; kk < BK / 8; ++kk) {
-                            const uint64_t adv = (uint64_t)(kk * 2);
-                            umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                            for (int kk = 0; kk < BK / 8; ++kk) {          // UMMA K = 8 tf32 = 32 bytes = +2 in descriptor units
+                                const uint64_t adv = (uint64_t)(kk * 2);
+                                umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
+                                umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                            }
+                            if (++st == STAGES) st = 0;
                         }
-                        umma_commit(bar_empty + 8 * stage);                // frees the smem slot when the MMAs retire
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        for (int j = 0; j < pair; ++j) {
+                            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                            const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < BK / 8; ++kk) {
+                                const uint64_t adv = (uint64_t)(kk * 2);
+                                umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                            }
+                            umma_commit(bar_empty + 8 * stage);            // frees the smem slot when the MMAs retire
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
                     }
                     umma_commit(bar_tfull + 8 * acc);                      // partial sum complete -> drain
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }

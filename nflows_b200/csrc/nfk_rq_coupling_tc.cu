@@ -92,8 +92,8 @@ __device__ __forceinline__ void rqs_eval_multi(const SplineParams& p, bool inver
     int bin[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) {
-        rw[f] = p.mix_w / sw[f];
-        rh[f] = p.mix_h / sh[f];
+        rw[f] = fast_div(p.mix_w, sw[f]);
+        rh[f] = fast_div(p.mix_h, sh[f]);
         cum_w[f] = 0.0f; cum_h[f] = 0.0f;
         kw_lo[f] = p.left; kh_lo[f] = p.bottom;
         b_cw[f] = p.left; b_ch[f] = p.bottom; b_w[f] = 1.0f; b_h[f] = 1.0f;
@@ -133,9 +133,9 @@ __device__ __forceinline__ void rqs_eval_multi(const SplineParams& p, bool inver
         }
 #pragma unroll
     for (int f = 0; f < F; ++f) {
-        const float d0 = p.min_d + softplus_torch(ud0[f], p.beta, p.inv_beta);
-        const float d1 = p.min_d + softplus_torch(ud1[f], p.beta, p.inv_beta);
-        const float delta = b_h[f] / b_w[f];
+        const float d0 = p.min_d + fast_softplus(ud0[f], p.beta, p.inv_beta);
+        const float d1 = p.min_d + fast_softplus(ud1[f], p.beta, p.inv_beta);
+        const float delta = fast_div(b_h[f], b_w[f]);
         const float s = d0 + d1 - 2.0f * delta;
         float theta, ys;
         if (inverse) {
@@ -145,20 +145,20 @@ __device__ __forceinline__ void rqs_eval_multi(const SplineParams& p, bool inver
             const float c = -delta * u;
             const float disc = b * b - 4.0f * a * c;
             if (!(disc >= 0.0f)) flag |= 2;
-            theta = (2.0f * c) / (-b - sqrtf(disc));
+            theta = fast_div(2.0f * c, -b - sqrtf(disc));
             ys = theta * b_w[f] + b_cw[f];
         } else {
-            theta = (x[f] - b_cw[f]) / b_w[f];
+            theta = fast_div(x[f] - b_cw[f], b_w[f]);
         }
         const float t1mt = theta * (1.0f - theta);
         const float den = delta + s * t1mt;
         if (!inverse) {
             const float num = b_h[f] * (delta * (theta * theta) + d0 * t1mt);
-            ys = b_ch[f] + num / den;
+            ys = b_ch[f] + fast_div(num, den);
         }
         const float omt = 1.0f - theta;
         const float dnum = (delta * delta) * (d1 * (theta * theta) + 2.0f * delta * t1mt + d0 * (omt * omt));
-        const float l = logf(dnum) - 2.0f * logf(den);
+        const float l = fast_log(dnum) - 2.0f * fast_log(den);
         const bool identity = TAILS && !inside[f];
         y[f] = identity ? xin[f] : ys;
         lad[f] = identity ? 0.0f : (inverse ? -l : l);
@@ -251,37 +251,40 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                             // issued before the first main product, so only the main MMAs round at full magnitude
                             const int slabs = min(DRAIN_SLABS, num_k - g * DRAIN_SLABS);
                             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-                            int st = stage; uint32_t ph = phase;
-                            for (int j = 0; j < slabs; ++j) {
-                                mbar_wait(bar_full + 8 * st, ph);
-                                if (++st == STAGES) { st = 0; ph ^= 1; }
-                            }
-                            tc_fence_after();
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-                            st = stage;
-                            for (int j = 0; j < slabs; ++j) {
-                                const uint32_t sa = smem_base + st * STAGE_BYTES;
-                                const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
-                                const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
-#pragma unroll
-                                for (int kk = 0; kk < BK / 8; ++kk) {
-                                    const uint64_t adv = (uint64_t)(kk * 2);
-                                    umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j | kk) != 0);
-                                    umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                            for (int j0 = 0; j0 < slabs; j0 += 2) {           // pairs of resident slabs: cross terms of both, then mains
+                                const int pair = min(2, slabs - j0);
+                                int st = stage; uint32_t ph = phase;
+                                for (int j = 0; j < pair; ++j) {
+                                    mbar_wait(bar_full + 8 * st, ph);
+                                    if (++st == STAGES) { st = 0; ph ^= 1; }
                                 }
-                                if (++st == STAGES) st = 0;
-                            }
-                            for (int j = 0; j < slabs; ++j) {
-                                const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                                const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
+                                tc_fence_after();
+                                st = stage;
+                                for (int j = 0; j < pair; ++j) {
+                                    const uint32_t sa = smem_base + st * STAGE_BYTES;
+                                    const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
+                                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                                for (int kk = 0; kk < BK / 8; ++kk) {
-                                    const uint64_t adv = (uint64_t)(kk * 2);
-                                    umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                                    for (int kk = 0; kk < BK / 8; ++kk) {
+                                        const uint64_t adv = (uint64_t)(kk * 2);
+                                        umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
+                                        umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                                    }
+                                    if (++st == STAGES) st = 0;
                                 }
-                                if (CL == 1) umma_commit(bar_empty + 8 * stage);
-                                else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // releases the slot in every CTA
-                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                for (int j = 0; j < pair; ++j) {
+                                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                                    const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
+#pragma unroll
+                                    for (int kk = 0; kk < BK / 8; ++kk) {
+                                        const uint64_t adv = (uint64_t)(kk * 2);
+                                        umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                                    }
+                                    if (CL == 1) umma_commit(bar_empty + 8 * stage);
+                                    else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // releases the slot in every CTA
+                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                }
                             }
                             umma_commit(bar_tfull + 8 * acc);
                             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -321,14 +324,14 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     if (ks == 0) {
                         // first partial of the tile: running sum = bias + partial (bias_packed is padded to whole tiles)
 #pragma unroll
-                        for (int c = 0; c < HC; c += 24) {             // 3 TMEM loads in flight per wait
-                            uint32_t raw[3][8];
+                        for (int c = 0; c < HC; c += 40) {             // 5 TMEM loads in flight per wait
+                            uint32_t raw[5][8];
 #pragma unroll
-                            for (int u = 0; u < 3; ++u)
+                            for (int u = 0; u < 5; ++u)
                                 if (c + 8 * u < HC) tmem_ld8(taddr + c + 8 * u, raw[u]);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int u = 0; u < 3; ++u)
+                            for (int u = 0; u < 5; ++u)
                                 if (c + 8 * u < HC) {
 #pragma unroll
                                     for (int i = 0; i < 8; ++i)
@@ -337,14 +340,14 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                         }
                     } else {
 #pragma unroll
-                        for (int c = 0; c < HC; c += 24) {
-                            uint32_t raw[3][8];
+                        for (int c = 0; c < HC; c += 40) {
+                            uint32_t raw[5][8];
 #pragma unroll
-                            for (int u = 0; u < 3; ++u)
+                            for (int u = 0; u < 5; ++u)
                                 if (c + 8 * u < HC) tmem_ld8(taddr + c + 8 * u, raw[u]);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int u = 0; u < 3; ++u)
+                            for (int u = 0; u < 5; ++u)
                                 if (c + 8 * u < HC) {
 #pragma unroll
                                     for (int i = 0; i < 8; i += 2) {       // packed fp32x2 round-to-nearest adds (FADD2)

@@ -56,6 +56,51 @@ NFK_HD float ex2_approx(float x) {
 #endif
 }
 
+// ---- cheap forms used on the epilogue critical path (NFK_SPLINE_FAST, default on).  Each replaces a ~10-30 instruction
+// IEEE/libm sequence by 2-6 instructions with <= ~2 ulp (division, log) error; the per-element effect (~1e-7 relative)
+// is below the fp32 round-off of the reference formulation (profiles/parity_calibration_*.txt, tests/test_kernel_source_on_host.py)
+#ifndef NFK_SPLINE_FAST
+#define NFK_SPLINE_FAST 1
+#endif
+
+NFK_HD float fast_div(float a, float b) {
+#if NFK_SPLINE_FAST
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);                       // MUFU.RCP + FMUL
+#else
+    return a * (1.0f / b);
+#endif
+#else
+    return a / b;
+#endif
+}
+
+NFK_HD float fast_log(float x) {
+#if NFK_SPLINE_FAST
+#ifdef __CUDA_ARCH__
+    return __logf(x);                              // MUFU.LG2 + FMUL
+#else
+    return log2f(x) * 0.693147180559945f;
+#endif
+#else
+    return logf(x);
+#endif
+}
+
+// softplus with F.softplus semantics (beta, threshold 20) = max(z,0) + log1p(exp(-|z|)), z = beta*x
+NFK_HD float fast_softplus(float x, float beta, float inv_beta) {
+#if NFK_SPLINE_FAST
+    const float z = x * beta;
+    const float t = ex2_approx(-fabsf(z) * 1.4426950408889634f);             // exp(-|z|) in (0, 1]
+    // log1p(t): short series where 1+t would lose the small t, MUFU log otherwise
+    const float l = t < 0.0078125f ? t * (1.0f - t * (0.5f - t * 0.33333334f)) : fast_log(1.0f + t);
+    const float sp = fmaxf(z, 0.0f) + l;
+    return z > 20.0f ? x : sp * inv_beta;
+#else
+    return softplus_torch(x, beta, inv_beta);
+#endif
+}
+
 // KMAX: compile-time bound on the number of bins (register arrays); p.num_bins <= KMAX.
 // uw/uh: K raw values (before the 1/sqrt(H) pre-scale); ud: K+1 raw derivative logits (already padded with
 // edge_ud for linear tails).  Returns y and log|dy/dx|; sets flag bits for domain / discriminant violations.
@@ -94,7 +139,7 @@ NFK_HD void rqs_eval(const SplineParams& p, bool inverse, float x_in, const floa
             sh += eh[k];
         }
     }
-    const float rw = p.mix_w / sw, rh = p.mix_h / sh;
+    const float rw = fast_div(p.mix_w, sw), rh = fast_div(p.mix_h, sh);
 
     // running prefix sums -> knots; select the bin on the fly
     float cum_w = 0.0f, cum_h = 0.0f;
@@ -124,9 +169,9 @@ NFK_HD void rqs_eval(const SplineParams& p, bool inverse, float x_in, const floa
         ud0 = (k == bin) ? ud[k] : ud0;
         ud1 = (k == bin) ? ud[k + 1] : ud1;
     }
-    const float d0 = p.min_d + softplus_torch(ud0, p.beta, p.inv_beta);
-    const float d1 = p.min_d + softplus_torch(ud1, p.beta, p.inv_beta);
-    const float delta = b_h / b_w;
+    const float d0 = p.min_d + fast_softplus(ud0, p.beta, p.inv_beta);
+    const float d1 = p.min_d + fast_softplus(ud1, p.beta, p.inv_beta);
+    const float delta = fast_div(b_h, b_w);
     const float s = d0 + d1 - 2.0f * delta;
 
     float theta, ys;
@@ -137,20 +182,20 @@ NFK_HD void rqs_eval(const SplineParams& p, bool inverse, float x_in, const floa
         const float c = -delta * u;
         const float disc = b * b - 4.0f * a * c;
         if (!(disc >= 0.0f)) flag |= 2;                   // reference: assert (discriminant >= 0).all() (:142)
-        theta = (2.0f * c) / (-b - sqrtf(disc));
+        theta = fast_div(2.0f * c, -b - sqrtf(disc));
         ys = theta * b_w + b_cw;
     } else {
-        theta = (x - b_cw) / b_w;
+        theta = fast_div(x - b_cw, b_w);
     }
     const float t1mt = theta * (1.0f - theta);
     const float den = delta + s * t1mt;
     if (!inverse) {
         const float num = b_h * (delta * (theta * theta) + d0 * t1mt);
-        ys = b_ch + num / den;
+        ys = b_ch + fast_div(num, den);
     }
     const float omt = 1.0f - theta;
     const float dnum = (delta * delta) * (d1 * (theta * theta) + 2.0f * delta * t1mt + d0 * (omt * omt));
-    const float l = logf(dnum) - 2.0f * logf(den);
+    const float l = fast_log(dnum) - 2.0f * fast_log(den);
     const bool identity = p.linear_tails && !inside;
     y = identity ? x_in : ys;
     lad = identity ? 0.0f : (inverse ? -l : l);
