@@ -268,6 +268,7 @@ def run_native(args):
             t[0] += a.elapsed_time(b)
             t[1] += 1
             t[2] += rows_k
+        result["timeline_ms_per_step"] = {k: round(v[0] / args.steps, 3) for k, v in sorted(tags.items(), key=lambda kv: -kv[1][0])}
         top = max(tags.items(), key=lambda kv: kv[1][0])
         tag, (tms, count, rows_k) = top
         flops = FLOP_FINAL_PER_ROW * rows_k

@@ -12,7 +12,7 @@
 // Accumulation: the tensor core adds into its fp32 accumulator with round-toward-zero, so a long chain of MMAs
 // acquires a bias of ~0.5 ulp per instruction (measured here: 2e-5 relative after the 294 MMAs of K=784, the same
 // effect Ootomo & Yokota 2022 report for Ampere).  The accumulator in TMEM therefore only ever holds a PARTIAL sum
-// over DRAIN_SLABS K-slabs (24 MMAs); the epilogue warps drain it with tcgen05.ld and keep the running sum in
+// over DRAIN_SLABS_LINEAR K-slabs (24 MMAs); the epilogue warps drain it with tcgen05.ld and keep the running sum in
 // registers with round-to-nearest FADDs, while the issuer continues into the other TMEM buffer.
 //
 // Kernel shape (one persistent CTA per SM, 384 threads; setmaxnreg moves registers from warpgroup 0 to 1-2):
@@ -73,7 +73,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int num_groups = (num_k + DRAIN_SLABS - 1) / DRAIN_SLABS;     // partial sums per tile
+    const int num_groups = (num_k + DRAIN_SLABS_LINEAR - 1) / DRAIN_SLABS_LINEAR;     // partial sums per tile
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");     // hand registers to the epilogue warpgroups
@@ -106,9 +106,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 for (int g = 0; g < num_groups; ++g) {
-                    // one partial sum = DRAIN_SLABS resident K-slabs; every small cross term (lo*hi, hi*lo) is issued before
+                    // one partial sum = DRAIN_SLABS_LINEAR resident K-slabs; every small cross term (lo*hi, hi*lo) is issued before
                     // the first main product, so only the main MMAs round at full magnitude
-                    const int slabs = min(DRAIN_SLABS, num_k - g * DRAIN_SLABS);
+                    const int slabs = min(DRAIN_SLABS_LINEAR, num_k - g * DRAIN_SLABS_LINEAR);
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);      // epilogue has drained this partial accumulator
                     const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                     for (int j0 = 0; j0 < slabs; j0 += 2) {               // pairs of resident slabs: cross terms of both, then mains
@@ -169,20 +169,24 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HALF;
 #pragma unroll
-                for (int c = 0; c < HALF; c += 16) {
-                    uint32_t raw[16];
-                    tmem_ld16(taddr + c, raw);
+                for (int c = 0; c < HALF; c += 64) {                       // two 32-column TMEM loads in flight per wait
+                    uint32_t raw[2][32];
+                    tmem_ld32(taddr + c, raw[0]);
+                    tmem_ld32(taddr + c + 32, raw[1]);
                     tmem_ld_wait();
-                    if (g == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) sum[c + j] = __uint_as_float(raw[j]);
-                    } else {
+                    for (int u = 0; u < 2; ++u) {
+                        if (g == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) {                  // packed fp32x2 round-to-nearest adds (FADD2)
-                            const float2 r2 = __fadd2_rn(make_float2(sum[c + j], sum[c + j + 1]),
-                                                         make_float2(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1])));
-                            sum[c + j] = r2.x;
-                            sum[c + j + 1] = r2.y;
+                            for (int j = 0; j < 32; ++j) sum[c + 32 * u + j] = __uint_as_float(raw[u][j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {              // packed fp32x2 round-to-nearest adds (FADD2)
+                                const float2 r2 = __fadd2_rn(make_float2(sum[c + 32 * u + j], sum[c + 32 * u + j + 1]),
+                                                             make_float2(__uint_as_float(raw[u][j]), __uint_as_float(raw[u][j + 1])));
+                                sum[c + 32 * u + j] = r2.x;
+                                sum[c + 32 * u + j + 1] = r2.y;
+                            }
                         }
                     }
                 }

@@ -188,7 +188,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (p.K + BK - 1) / BK;
-    const int num_groups = (num_k + DRAIN_SLABS - 1) / DRAIN_SLABS;     // partial sums per tile
+    const int num_groups = (num_k + DRAIN_SLABS_FUSED - 1) / DRAIN_SLABS_FUSED;     // partial sums per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
@@ -239,7 +239,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 }
             }
         } else if (warp == 1) {
-            // ================================================= MMA issuer (one thread): one partial sum per DRAIN_SLABS slabs
+            // ================================================= MMA issuer (one thread): one partial sum per DRAIN_SLABS_FUSED slabs
             if (lane == 0) {
                 const uint32_t idesc = make_idesc(BN);
                 int stage = 0; uint32_t phase = 0;
@@ -247,9 +247,9 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 for (int mb = first_block; mb < num_blocks; mb += block_step) {
                     for (int n = 0; n < p.num_n_tiles; ++n) {
                         for (int g = 0; g < num_groups; ++g) {
-                            // one partial sum = DRAIN_SLABS resident K-slabs; every small cross term (lo*hi, hi*lo) is
+                            // one partial sum = DRAIN_SLABS_FUSED resident K-slabs; every small cross term (lo*hi, hi*lo) is
                             // issued before the first main product, so only the main MMAs round at full magnitude
-                            const int slabs = min(DRAIN_SLABS, num_k - g * DRAIN_SLABS);
+                            const int slabs = min(DRAIN_SLABS_FUSED, num_k - g * DRAIN_SLABS_FUSED);
                             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                             for (int j0 = 0; j0 < slabs; j0 += 2) {           // pairs of resident slabs: cross terms of both, then mains

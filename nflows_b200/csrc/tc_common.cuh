@@ -13,7 +13,9 @@ constexpr int BN_MAX = 256;        // columns per tile (runtime BN <= BN_MAX, mu
 constexpr int BK = 16;             // fp32 elements per K-slab = one 64-byte swizzle row (SWIZZLE_64B)
 constexpr int STAGES = 4;          // 4 x 48 KB slabs: 3 TMA loads in flight while one slab is consumed
 constexpr int THREADS = 384;        // warpgroup 0: TMA + MMA warps (2 idle); warpgroups 1-2: accumulate/epilogue
-constexpr int DRAIN_SLABS = 4;       // K-slabs accumulated inside the tensor core before a drain (K = 64: 24 MMAs)
+// K-slabs accumulated inside the tensor core before the partial sum is drained to registers (precision vs drain cost):
+constexpr int DRAIN_SLABS_LINEAR = 2;   // dense layers: K = 32 (12 MMAs) -- their outputs feed log p directly
+constexpr int DRAIN_SLABS_FUSED = 4;    // fused coupling: K = 64 (24 MMAs) -- its outputs are spline logits
 constexpr int HALF = BN_MAX / 2;     // columns per epilogue warp
 constexpr int A_BYTES = BM * BK * 4;             // 16 KB
 constexpr int B_BYTES = BN_MAX * BK * 4;         // 32 KB

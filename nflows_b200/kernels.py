@@ -161,6 +161,12 @@ def split_tf32(x, cols_i32=None, relu=False, copy_to=None):
     c = x.shape[1] if cols_i32 is None else cols_i32.numel()
     hi = torch.empty(n, c, dtype=torch.float32, device=x.device)
     lo = torch.empty_like(hi)
+    if TIMELINE is not None:
+        with timed("split_%d" % c, n):
+            N.check(N.lib().nfk_split_tf32(x.data_ptr(), x.stride(0), N.ptr(cols_i32), c, int(relu), hi.data_ptr(), lo.data_ptr(),
+                                           hi.stride(0), N.ptr(copy_to), copy_to.stride(0) if copy_to is not None else 0, n,
+                                           N.stream()))
+        return hi, lo
     N.check(N.lib().nfk_split_tf32(x.data_ptr(), x.stride(0), N.ptr(cols_i32), c, int(relu), hi.data_ptr(), lo.data_ptr(),
                                    hi.stride(0), N.ptr(copy_to), copy_to.stride(0) if copy_to is not None else 0, n,
                                    N.stream()))
@@ -184,6 +190,14 @@ def linear_tf32x3(a_pair, w_pair, bias=None, residual=None, relu_out=False, want
         if want_split else None
     if bias is not None and not bias.is_contiguous():
         bias = bias.contiguous()
+    if TIMELINE is not None:
+        with timed("linear_%dx%d" % (k, o), n):
+            N.check(N.lib().nfk_linear_tf32x3(
+                a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N.ptr(bias),
+                N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y), y.stride(0) if y is not None else 0,
+                N.ptr(pair[0]) if pair else 0, N.ptr(pair[1]) if pair else 0, pair[0].stride(0) if pair else 0, int(relu_out),
+                int(split_relu), n, k, o, N.stream()))
+        return y, pair
     N.check(N.lib().nfk_linear_tf32x3(
         a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N.ptr(bias),
         N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y), y.stride(0) if y is not None else 0,

@@ -398,7 +398,7 @@ def test_fused_coupling_kernel_matches_unfused_and_oracle(cuda_device, bins, tai
             config.fuse_coupling = True
             monkeypatch.delenv("NFLOWS_B200_GEMM")
         tol_y = max(TOL, 3 * rel_err(want_y, truth_y))
-        tol_l = max(3e-5, 3 * rel_err(want_l, truth_l))
+        tol_l = max(3e-5, 5 * rel_err(want_l, truth_l))
         assert rel_err(y1.cpu(), truth_y) <= tol_y and rel_err(y2.cpu(), truth_y) <= tol_y, (bins, tails, inverse)
         assert rel_err(l1.cpu(), truth_l) <= tol_l and rel_err(l2.cpu(), truth_l) <= tol_l, (bins, tails, inverse)
         idf = sd["identity_features"].to(cuda_device)
