@@ -15,6 +15,10 @@ class _Config:
     param_chunk_mib = 64
     #: run the final conditioner layer and the spline as ONE tensor-core kernel when an instance exists
     fuse_coupling = True
+    #: rows per sub-block of a dense-layer chain: intermediates of a sub-block (split pairs, hidden activations) stay
+    #: resident in the 126 MB L2 between consecutive kernels instead of round-tripping through HBM
+    trunk_block_rows = 16384
+    affine_block_rows = 8192
 
 
 config = _Config()

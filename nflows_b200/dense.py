@@ -7,6 +7,8 @@ Two kernels implement the same contract (fp32-equivalent products, fp32 accumula
 Both are CUDA kernels of this library; there is no PyTorch/cuBLAS path here."""
 import os
 
+import torch
+
 from . import kernels as K
 
 _SPLIT_CACHE = {}
@@ -52,7 +54,24 @@ class ChainState:
 
 def run_trunk(chain, x, id_cols, use_tc, copy_identity_to=None):
     """All layers of `chain` but the last, on the identity columns of x.  Returns the ChainState feeding the last layer.
-    copy_identity_to: coupling output whose identity columns are filled on the way (tensor-core path only)."""
+    copy_identity_to: coupling output whose identity columns are filled on the way (tensor-core path only).
+    The tensor-core path walks row sub-blocks so that every intermediate of a sub-block stays L2-resident."""
+    from . import config
+    n = x.shape[0]
+    step = max(128, int(config.trunk_block_rows))
+    if use_tc and n > step and len(chain) > 1:
+        width = chain[-2][0].shape[0]
+        hi = torch.empty(n, width, dtype=torch.float32, device=x.device)
+        lo = torch.empty_like(hi)
+        for r0 in range(0, n, step):
+            r1 = min(n, r0 + step)
+            sub = _run_trunk_block(chain, x[r0:r1], id_cols, True,
+                                   None if copy_identity_to is None else copy_identity_to[r0:r1], (hi[r0:r1], lo[r0:r1]))
+        return ChainState(raw=None, pair=(hi, lo))
+    return _run_trunk_block(chain, x, id_cols, use_tc, copy_identity_to, None)
+
+
+def _run_trunk_block(chain, x, id_cols, use_tc, copy_identity_to, last_pair_out):
     body = chain[:-1]
     last_relu_in = chain[-1][2]
     if use_tc:
@@ -65,7 +84,8 @@ def run_trunk(chain, x, id_cols, use_tc, copy_identity_to=None):
             res = skip_src if residual == "skip" else None
             y, pair = K.linear_tf32x3(state.pair, split_weight(weight), bias.detach() if bias is not None else None,
                                       residual=res, relu_out=relu_out, want_y=need_raw, want_split=True,
-                                      split_relu=nxt_relu_in)
+                                      split_relu=nxt_relu_in,
+                                      pair_out=last_pair_out if i == len(body) - 1 else None)
             if need_raw:
                 skip_src = y
             state = ChainState(raw=y, pair=pair)
@@ -94,10 +114,18 @@ def run_last(chain, state, r0, r1, use_tc):
 
 
 def affine_map(x, weight, bias):
-    """y = x @ weight.T + bias for a folded ActNorm/Permutation/LU run."""
-    k = x.shape[1]
+    """y = x @ weight.T + bias for a folded ActNorm/Permutation/LU run, in row sub-blocks small enough that the split pair
+    written by `split_tf32` is still in L2 when the GEMM reads it."""
+    from . import config
+    n, k = x.shape
     if backend() == "tc" and K.tf32x3_supported(x.stride(0), weight.stride(0), k):
-        return K.linear_tf32x3(K.split_tf32(x), split_weight(weight), bias, want_y=True)[0]
+        w_pair = split_weight(weight)
+        y = torch.empty(n, weight.shape[0], dtype=torch.float32, device=x.device)
+        step = max(128, int(config.affine_block_rows))
+        for r0 in range(0, n, step):
+            r1 = min(n, r0 + step)
+            K.linear_tf32x3(K.split_tf32(x[r0:r1]), w_pair, bias, want_y=True, y_out=y[r0:r1])
+        return y
     return K.linear(x, weight, bias)
 
 

@@ -178,16 +178,20 @@ def tf32x3_supported(lda, ldw, in_features):
 
 
 def linear_tf32x3(a_pair, w_pair, bias=None, residual=None, relu_out=False, want_y=True, want_split=False,
-                  split_relu=False):
-    """tcgen05 dense layer on split operands.  Returns (y or None, (y_hi, y_lo) or None)."""
+                  split_relu=False, y_out=None, pair_out=None):
+    """tcgen05 dense layer on split operands.  Returns (y or None, (y_hi, y_lo) or None); y_out / pair_out are
+    caller-provided destinations (row slices of larger buffers)."""
     a_hi, a_lo = a_pair
     w_hi, w_lo = w_pair
     n, k = a_hi.shape
     o = w_hi.shape[0]
     dev = a_hi.device
-    y = torch.empty(n, o, dtype=torch.float32, device=dev) if want_y else None
-    pair = (torch.empty(n, o, dtype=torch.float32, device=dev), torch.empty(n, o, dtype=torch.float32, device=dev)) \
-        if want_split else None
+    y = (y_out if y_out is not None else torch.empty(n, o, dtype=torch.float32, device=dev)) if want_y else None
+    if want_split:
+        pair = pair_out if pair_out is not None else (torch.empty(n, o, dtype=torch.float32, device=dev),
+                                                      torch.empty(n, o, dtype=torch.float32, device=dev))
+    else:
+        pair = None
     if bias is not None and not bias.is_contiguous():
         bias = bias.contiguous()
     if TIMELINE is not None:
