@@ -17,8 +17,10 @@ class _Config:
     fuse_coupling = True
     #: rows per sub-block of a dense-layer chain: intermediates of a sub-block (split pairs, hidden activations) stay
     #: resident in the 126 MB L2 between consecutive kernels instead of round-tripping through HBM
-    trunk_block_rows = 16384
-    affine_block_rows = 8192
+    #: (measured r1: sub-blocks of 8-16 K rows are SLOWER -- 1-wave launches pay prologue/launch overhead -- so the default
+    #: keeps whole 256 K-row blocks; the knob stays for a future persistent / graph-captured executor)
+    trunk_block_rows = 1 << 18
+    affine_block_rows = 1 << 18
 
 
 config = _Config()

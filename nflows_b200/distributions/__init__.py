@@ -1,2 +1,2 @@
 from .base import Distribution, NoMeanException
-from .normal import StandardNormal
+from .normal import ConditionalDiagonalNormal, DiagonalNormal, StandardNormal

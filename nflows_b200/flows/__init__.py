@@ -1,1 +1,3 @@
 from .base import Flow
+from .realnvp import SimpleRealNVP
+from . import realnvp

@@ -4,7 +4,10 @@ from .coupling import (AdditiveCouplingTransform, AffineCouplingTransform, Coupl
                        PiecewiseCouplingTransform, PiecewiseRationalQuadraticCouplingTransform)
 from .linear import Linear
 from .lu import LULinear
-from .normalization import ActNorm
+from .normalization import ActNorm, BatchNorm
+from .conv import OneByOneConvolution
+from .nonlinearities import PiecewiseRationalQuadraticCDF
+from .reshape import SqueezeTransform
 from .permutations import Permutation, RandomPermutation, ReversePermutation
 from .standard import AffineScalarTransform, AffineTransform, IdentityTransform, PointwiseAffineTransform
 from . import splines

@@ -86,8 +86,7 @@ class CouplingTransform(Transform):
 
     # ---- native path --------------------------------------------------------------------------------------
     def _native_ready(self, inputs, context):
-        return (K.native_ok(inputs) and inputs.dim() == 2 and self.unconditional_transform is None
-                and params_frozen(self) and self._native_epilogue_supported())
+        return K.native_ok(inputs) and inputs.dim() == 2 and params_frozen(self) and self._native_epilogue_supported()
 
     def _native_epilogue_supported(self):
         return False
@@ -107,6 +106,24 @@ class CouplingTransform(Transform):
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
         self._check_inputs(inputs)
+        if self.unconditional_transform is None:
+            return self._native_coupling(inputs, lad, flags, inverse, context)
+        # identity half additionally goes through its own elementwise transform (coupling.py:90-94 forward: after the
+        # conditioner has seen the untouched identity half; :114-118 inverse: before the conditioner)
+        idf = self.identity_features
+        if inverse:
+            identity, lad_id = self.unconditional_transform.inverse(inputs[:, idf], context)
+            staged = inputs.clone()
+            staged[:, idf] = identity
+            outputs = self._native_coupling(staged, lad, flags, True, context)
+        else:
+            outputs = self._native_coupling(inputs, lad, flags, False, context)
+            identity, lad_id = self.unconditional_transform(inputs[:, idf], context)
+            outputs[:, idf] = identity
+        lad += lad_id
+        return outputs
+
+    def _native_coupling(self, inputs, lad, flags, inverse, context=None):
         id_cols, t_cols = self._cols(inputs.device)
         n = inputs.shape[0]
         outputs = torch.empty_like(inputs, memory_format=torch.contiguous_format)

@@ -1,10 +1,12 @@
-"""ActNorm (reference nflows/transforms/normalization.py:144-218)."""
+"""ActNorm and BatchNorm transforms (reference nflows/transforms/normalization.py:72-218)."""
+import numpy as np
 import torch
 from torch import nn
+from torch.nn import functional as F
 
 from .. import kernels as K
 from ..utils import typechecks as check
-from .base import Transform, params_frozen
+from .base import InverseNotAvailable, Transform, params_frozen
 
 
 class ActNorm(Transform):
@@ -60,3 +62,46 @@ class ActNorm(Transform):
             self.log_scale.data = -torch.log(std)
             self.shift.data = -mu
             self.initialized.data = torch.tensor(True, dtype=torch.bool)
+
+
+class BatchNorm(Transform):
+    """Batch normalisation as an invertible transform on feature vectors (reference :72-141): batch statistics in training
+    mode (running statistics updated with `momentum`), running statistics in eval mode, where it is a fixed per-feature
+    affine map and therefore invertible.  Torch path only: it is not on the hot path."""
+
+    def __init__(self, features, eps=1e-5, momentum=0.1, affine=True):
+        if not check.is_positive_int(features):
+            raise TypeError("Number of features must be a positive integer.")
+        super().__init__()
+        self.momentum = momentum
+        self.eps = eps
+        self.unconstrained_weight = nn.Parameter(np.log(np.exp(1 - eps) - 1) * torch.ones(features))
+        self.bias = nn.Parameter(torch.zeros(features))
+        self.register_buffer("running_mean", torch.zeros(features))
+        self.register_buffer("running_var", torch.zeros(features))
+
+    @property
+    def weight(self):
+        return F.softplus(self.unconstrained_weight) + self.eps
+
+    def forward(self, inputs, context=None):
+        if inputs.dim() != 2:
+            raise ValueError("Expected 2-dim inputs, got inputs of shape: {}".format(inputs.shape))
+        if self.training:
+            mean, var = inputs.mean(0), inputs.var(0)
+            self.running_mean.mul_(1 - self.momentum).add_(mean.detach() * self.momentum)
+            self.running_var.mul_(1 - self.momentum).add_(var.detach() * self.momentum)
+        else:
+            mean, var = self.running_mean, self.running_var
+        outputs = self.weight * ((inputs - mean) / torch.sqrt(var + self.eps)) + self.bias
+        logabsdet = torch.sum(torch.log(self.weight) - 0.5 * torch.log(var + self.eps))
+        return outputs, logabsdet * inputs.new_ones(inputs.shape[0])
+
+    def inverse(self, inputs, context=None):
+        if self.training:
+            raise InverseNotAvailable("Batch norm inverse is only available in eval mode, not in training mode.")
+        if inputs.dim() != 2:
+            raise ValueError("Expected 2-dim inputs, got inputs of shape: {}".format(inputs.shape))
+        outputs = torch.sqrt(self.running_var + self.eps) * ((inputs - self.bias) / self.weight) + self.running_mean
+        logabsdet = torch.sum(-torch.log(self.weight) + 0.5 * torch.log(self.running_var + self.eps))
+        return outputs, logabsdet * inputs.new_ones(inputs.shape[0])

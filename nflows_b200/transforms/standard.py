@@ -45,8 +45,12 @@ class PointwiseAffineTransform(Transform):
 
 
 class AffineTransform(PointwiseAffineTransform):
+    """Deprecated alias kept by the reference (standard.py:70-86); `None` means "default"."""
+
     def __init__(self, shift=0.0, scale=1.0):
-        super().__init__(shift, scale)
+        import warnings
+        warnings.warn("Use PointwiseAffineTransform", DeprecationWarning)
+        super().__init__(0.0 if shift is None else shift, 1.0 if scale is None else scale)
 
 
 AffineScalarTransform = AffineTransform

@@ -76,3 +76,14 @@ def searchsorted(bin_locations, inputs, eps=1e-6):
     eps IN PLACE so the right edge belongs to the last bin."""
     bin_locations[..., -1] += eps
     return torch.sum(inputs[..., None] >= bin_locations, dim=-1) - 1
+
+
+def random_orthogonal(size):
+    """Random orthogonal [size, size] matrix (Q factor of a Gaussian matrix)."""
+    q, _ = torch.linalg.qr(torch.randn(size, size))
+    return q
+
+
+def cbrt(x):
+    """Real cube root."""
+    return torch.sign(x) * torch.exp(torch.log(torch.abs(x)) / 3.0)

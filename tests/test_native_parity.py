@@ -403,3 +403,52 @@ def test_fused_coupling_kernel_matches_unfused_and_oracle(cuda_device, bins, tai
         assert rel_err(l1.cpu(), truth_l) <= tol_l and rel_err(l2.cpu(), truth_l) <= tol_l, (bins, tails, inverse)
         idf = sd["identity_features"].to(cuda_device)
         assert torch.equal(y1[:, idf], xd[:, idf]) and torch.equal(y2[:, idf], xd[:, idf])
+
+
+@torch.no_grad()
+def test_next_rows_native_vs_torch_path(cuda_device):
+    """SURVEY section 8 'next' rows that already run on our kernels: 1x1 convolution (folded LU dense layer per pixel),
+    unconditional RQ CDF (batch-shared spline parameters), apply_unconditional_transform couplings, SimpleRealNVP.
+    The CUDA result is compared with the same module's torch path on CPU (itself pinned by the reference's unit tests,
+    tests/test_reference_suite_compat.py)."""
+    from nflows_b200.flows import SimpleRealNVP
+    torch.manual_seed(0)
+    conv = T.OneByOneConvolution(12, identity_init=False).eval()
+    x = torch.randn(5, 12, 6, 6)
+    want, wl = conv(x)
+    with native_launches():
+        got, gl = conv.to(cuda_device)(x.to(cuda_device))
+    assert rel_err(got.cpu(), want) <= TOL and rel_err(gl.cpu(), wl) <= TOL
+    back, bl = conv.inverse(got)
+    assert rel_err(back.cpu(), x) <= 1e-4 and rel_err((gl + bl).cpu(), torch.zeros(5)) <= 1e-4
+
+    for tails in (None, "linear"):
+        cdf = T.PiecewiseRationalQuadraticCDF(shape=[7], num_bins=6, tails=tails, tail_bound=2.0).eval()
+        x = torch.rand(300, 7) if tails is None else torch.randn(300, 7) * 1.5
+        want, wl = cdf(x)
+        with native_launches():
+            got, gl = cdf.to(cuda_device)(x.to(cuda_device))
+        assert rel_err(got.cpu(), want) <= TOL and rel_err(gl.cpu(), wl) <= 3e-5
+        back, _ = cdf.inverse(got)
+        assert rel_err(back.cpu(), x) <= 1e-4
+
+    t = T.PiecewiseRationalQuadraticCouplingTransform(
+        torchutils.create_alternating_binary_mask(16), lambda i, o: ResidualNet(i, o, hidden_features=32, num_blocks=1),
+        num_bins=8, tails="linear", tail_bound=3.0, apply_unconditional_transform=True).eval()
+    x = torch.randn(200, 16) * 1.2
+    want, wl = t(x)
+    wi, wil = t.inverse(x)
+    t = t.to(cuda_device)
+    with native_launches():
+        got, gl = t(x.to(cuda_device))
+    assert rel_err(got.cpu(), want) <= TOL and rel_err(gl.cpu(), wl) <= 3e-5
+    gi, gil = t.inverse(x.to(cuda_device))
+    assert rel_err(gi.cpu(), wi) <= 1e-4 and rel_err(gil.cpu(), wil) <= 1e-4
+
+    flow = SimpleRealNVP(features=10, hidden_features=16, num_layers=3, num_blocks_per_layer=2).eval()
+    x = torch.randn(257, 10)
+    want = flow.log_prob(x)
+    with native_launches():
+        got = flow.to(cuda_device).log_prob(x.to(cuda_device))
+    assert rel_err(got.cpu(), want) <= TOL
+    assert flow.sample(9).shape == (9, 10)
