@@ -77,6 +77,10 @@ __global__ void __launch_bounds__(256) rqs_elementwise_kernel(SplineParams p, in
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kRowsThreads = 128;
 
+// One block = 128 threads = 128 consecutive (row, feature) elements per chunk.  The parameters of a chunk are one
+// contiguous run of 128*M floats: they are fetched with coalesced 16-byte loads into REGISTERS one chunk ahead (so the
+// HBM latency of chunk c+1 is covered by the arithmetic of chunk c), parked in shared memory, and read back one element per
+// thread (stride M words: conflict-free for odd M).
 template <int KMAX>
 __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, int inverse, const float* __restrict__ x,
                                                                 int64_t ldx, const float* __restrict__ params,
@@ -86,92 +90,146 @@ __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, 
                                                                 float* __restrict__ lad_accum, int64_t n_rows,
                                                                 int rows_per_group, int32_t* flags) {
     extern __shared__ __align__(16) float sp[];   // [kRowsThreads * M] staged parameters, then [kRowsThreads] lad
+    // float4 per thread staged in registers = ceil(M_max / 4); register prefetch only for the common small bin counts
+    constexpr int kMaxPrefetch = KMAX <= 16 ? (3 * KMAX + 1 + 3) / 4 : 1;
     const int K = p.num_bins;
     const int M = p.linear_tails ? 3 * K - 1 : 3 * K + 1;
     float* s_lad = sp + kRowsThreads * M;
     const int tid = threadIdx.x;
     const int64_t n_groups = (n_rows + rows_per_group - 1) / rows_per_group;
+    const bool pow2_rows = rows_per_group > 1 && (d_t & (d_t - 1)) == 0 && d_t <= 32;   // a row = an aligned lane group
+    const bool use_prefetch = KMAX <= 16 && (kRowsThreads * M + 3) / 4 <= kMaxPrefetch * kRowsThreads;
     int flag = 0;
 
-    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    float4 pre[kMaxPrefetch];
+    // chunk (g, e0): elements [e0, e0 + cnt) of row group g
+    auto chunk_src = [&](int64_t g, int e0) { return params + ((g * rows_per_group) * d_t + e0) * (int64_t)M; };
+    auto chunk_cnt = [&](int64_t g, int e0) {
+        const int rows_here = (int)min((int64_t)rows_per_group, n_rows - g * rows_per_group);
+        return min(kRowsThreads, rows_here * d_t - e0);
+    };
+    auto prefetch = [&](const float* src, int n_f) {
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+        for (int u = 0; u < kMaxPrefetch; ++u) {
+            const int i = tid + u * kRowsThreads;
+            if (i < (n_f >> 2)) pre[u] = __ldcs(src4 + i);
+        }
+    };
+    auto park = [&](const float* src, int n_f, bool fetched) {
+        if (fetched) {
+            float4* dst4 = reinterpret_cast<float4*>(sp);
+#pragma unroll
+            for (int u = 0; u < kMaxPrefetch; ++u) {
+                const int i = tid + u * kRowsThreads;
+                if (i < (n_f >> 2)) dst4[i] = pre[u];
+            }
+            for (int i = (n_f & ~3) + tid; i < n_f; i += kRowsThreads) sp[i] = __ldcs(src + i);
+        } else {
+            for (int i = tid; i < n_f; i += kRowsThreads) sp[i] = __ldcs(src + i);
+        }
+    };
+
+    int64_t g = blockIdx.x;
+    int e0 = 0;
+    bool have = false;               // registers hold the chunk (g, e0)
+    if (g < n_groups) {
+        const float* src = chunk_src(g, e0);
+        have = use_prefetch && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+        if (have) prefetch(src, chunk_cnt(g, e0) * M);
+    }
+    float my_lad = 0.0f;
+    while (g < n_groups) {
         const int64_t row0 = g * rows_per_group;
         const int rows_here = (int)min((int64_t)rows_per_group, n_rows - row0);
         const int n_el = rows_here * d_t;
-        float my_lad = 0.0f;
+        const int cnt = min(kRowsThreads, n_el - e0);
+        park(chunk_src(g, e0), cnt * M, have);
+        __syncthreads();
+        // next chunk: same group if it has more elements, else the next group of this block
+        int64_t ng = g;
+        int ne0 = e0 + kRowsThreads;
+        if (ne0 >= n_el) { ng = g + gridDim.x; ne0 = 0; }
+        have = false;
+        if (ng < n_groups) {
+            const float* nsrc = chunk_src(ng, ne0);
+            have = use_prefetch && ((reinterpret_cast<uintptr_t>(nsrc) & 15u) == 0);
+            if (have) prefetch(nsrc, chunk_cnt(ng, ne0) * M);
+        }
 
-        for (int e0 = 0; e0 < n_el; e0 += kRowsThreads) {
-            const int cnt = min(kRowsThreads, n_el - e0);
-            const float* src = params + (row0 * d_t + e0) * (int64_t)M;
-            const int n_f = cnt * M;
-            if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
-                const float4* src4 = reinterpret_cast<const float4*>(src);
-                float4* dst4 = reinterpret_cast<float4*>(sp);
-                for (int i = tid; i < (n_f >> 2); i += kRowsThreads) dst4[i] = __ldcs(src4 + i);
-                for (int i = (n_f & ~3) + tid; i < n_f; i += kRowsThreads) sp[i] = __ldcs(src + i);
+        float ll = 0.0f;
+        if (tid < cnt) {
+            const int e = e0 + tid;
+            const int r = e / d_t;
+            const int j = e - r * d_t;
+            const int col = t_cols ? t_cols[j] : j;
+            const int64_t row = row0 + r;
+            const float* q = sp + tid * M;
+            float w[KMAX], h[KMAX], d[KMAX + 1];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                w[k] = (k < K) ? q[k] : 0.0f;
+                h[k] = (k < K) ? q[K + k] : 0.0f;
+            }
+            if (p.linear_tails) {
+#pragma unroll
+                for (int k = 0; k <= KMAX; ++k) d[k] = (k >= 1 && k < K) ? q[2 * K + k - 1] : p.edge_ud;
             } else {
-                for (int i = tid; i < n_f; i += kRowsThreads) sp[i] = __ldcs(src + i);
+#pragma unroll
+                for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? q[2 * K + k] : 0.0f;
             }
-            __syncthreads();
-            float ll = 0.0f;
-            if (tid < cnt) {
-                const int e = e0 + tid;
-                const int r = e / d_t;
-                const int j = e - r * d_t;
-                const int col = t_cols ? t_cols[j] : j;
-                const int64_t row = row0 + r;
-                const float* q = sp + tid * M;
-                float w[KMAX], h[KMAX], d[KMAX + 1];
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k) {
-                    w[k] = (k < K) ? q[k] : 0.0f;
-                    h[k] = (k < K) ? q[K + k] : 0.0f;
-                }
-                if (p.linear_tails) {
-#pragma unroll
-                    for (int k = 0; k <= KMAX; ++k) d[k] = (k >= 1 && k < K) ? q[2 * K + k - 1] : p.edge_ud;
-                } else {
-#pragma unroll
-                    for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? q[2 * K + k] : 0.0f;
-                }
-                float yy;
-                rqs_eval<KMAX>(p, inverse != 0, x[row * ldx + col], w, h, d, yy, ll, flag);
-                y[row * ldy + col] = yy;
-            }
-            if (rows_per_group > 1) s_lad[tid] = ll; else my_lad += ll;
-            __syncthreads();
+            float yy;
+            rqs_eval<KMAX>(p, inverse != 0, x[row * ldx + col], w, h, d, yy, ll, flag);
+            y[row * ldy + col] = yy;
         }
 
-        // identity columns: bit-exact copy (coupling.py:96-97)
-        for (int e = tid; e < rows_here * d_id; e += kRowsThreads) {
-            const int r = e / d_id;
-            const int col = id_cols[e - r * d_id];
-            y[(row0 + r) * ldy + col] = x[(row0 + r) * ldx + col];
+        if (rows_per_group == 1) {
+            my_lad += ll;
+        } else if (pow2_rows) {
+            // a row is d_t consecutive lanes inside one warp: butterfly over the lane group, fixed order
+            float v = ll;
+            for (int o = d_t >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lad_accum && tid < cnt && (tid & (d_t - 1)) == 0) lad_accum[row0 + tid / d_t] += v;
+        } else {
+            s_lad[tid] = ll;
         }
+        __syncthreads();
 
-        if (lad_accum) {
-            if (rows_per_group > 1) {
-                // single chunk by construction (rows_per_group * d_t <= kRowsThreads): fixed-order per-row sums
-                if (tid < rows_here) {
-                    float s = 0.0f;
-                    for (int j = 0; j < d_t; ++j) s += s_lad[tid * d_t + j];
-                    lad_accum[row0 + tid] += s;
-                }
-                __syncthreads();
-            } else {
-                // deterministic block tree reduction
-                float v = my_lad;
+        const bool group_done = (ne0 == 0);
+        if (group_done) {
+            // identity columns: bit-exact copy (coupling.py:96-97)
+            for (int e = tid; e < rows_here * d_id; e += kRowsThreads) {
+                const int r = e / d_id;
+                const int col = id_cols[e - r * d_id];
+                y[(row0 + r) * ldy + col] = x[(row0 + r) * ldx + col];
+            }
+            if (lad_accum) {
+                if (rows_per_group == 1) {
+                    float v = my_lad;                 // deterministic block tree reduction
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if ((tid & 31) == 0) s_lad[tid >> 5] = v;
-                __syncthreads();
-                if (tid == 0) {
-                    float s = 0.0f;
-                    for (int w = 0; w < kRowsThreads / 32; ++w) s += s_lad[w];
-                    lad_accum[row0] += s;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if ((tid & 31) == 0) s_lad[tid >> 5] = v;
+                    __syncthreads();
+                    if (tid == 0) {
+                        float t = 0.0f;
+                        for (int w = 0; w < kRowsThreads / 32; ++w) t += s_lad[w];
+                        lad_accum[row0] += t;
+                    }
+                    __syncthreads();
+                    my_lad = 0.0f;
+                } else if (!pow2_rows) {
+                    // single chunk by construction (rows_per_group * d_t <= kRowsThreads): fixed-order per-row sums
+                    if (tid < rows_here) {
+                        float t = 0.0f;
+                        for (int j = 0; j < d_t; ++j) t += s_lad[tid * d_t + j];
+                        lad_accum[row0 + tid] += t;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         }
+        g = ng;
+        e0 = ne0;
     }
     if (flag && flags) atomicOr(flags, flag);
 }
