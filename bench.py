@@ -129,7 +129,7 @@ def spline_hbm_roofline(dev, peaks, rows=1 << 20, d_t=32, bins=8, iters=10):
     ms = e0.elapsed_time(e1) / iters
     nbytes = rows * (d_t * (4 * (m + 2)) + d_t * 8 + 8)
     achieved = nbytes / (ms * 1e-3) / 1e9
-    return {"kernel": "rqs_rows_kernel<8>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    return {"kernel": "rqs_rows_kernel<8,exact>", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / peaks["hbm_gbs"], "traffic": None, "avg_launch_ms": ms,
             "workload": "rows=2^20 d_t=32 K=8 params in HBM (3.2 GB > L2)", "peak_kind": "copy bandwidth, %s" % peaks["source"]}
 

@@ -37,14 +37,14 @@ int make_spline_params(const NfkSplineDesc* d, SplineParams* p) {
 // ------------------------------------------------------------------------------------------------------------
 // elementwise API: one thread per element, parameters read straight from global memory
 // ------------------------------------------------------------------------------------------------------------
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __global__ void __launch_bounds__(256) rqs_elementwise_kernel(SplineParams p, int inverse, const float* __restrict__ x,
                                                               const float* __restrict__ uw, const float* __restrict__ uh,
                                                               const float* __restrict__ ud, int64_t stride_w,
                                                               int64_t stride_h, int64_t stride_d, int64_t period,
                                                               float* __restrict__ y, float* __restrict__ lad,
                                                               int64_t n_elem, int32_t* flags) {
-    const int K = p.num_bins;
+    const int K = EXACT ? KMAX : p.num_bins;
     int flag = 0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = period > 0 ? e % period : e;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) rqs_elementwise_kernel(SplineParams p, in
             for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? __ldg(pd + k) : 0.0f;
         }
         float yy, ll;
-        rqs_eval<KMAX>(p, inverse != 0, x[e], w, h, d, yy, ll, flag);
+        rqs_eval<KMAX, EXACT>(p, inverse != 0, x[e], w, h, d, yy, ll, flag);
         y[e] = yy;
         lad[e] = ll;
     }
@@ -81,7 +81,7 @@ constexpr int kRowsThreads = 128;
 // contiguous run of 128*M floats: they are fetched with coalesced 16-byte loads into REGISTERS one chunk ahead (so the
 // HBM latency of chunk c+1 is covered by the arithmetic of chunk c), parked in shared memory, and read back one element per
 // thread (stride M words: conflict-free for odd M).
-template <int KMAX>
+template <int KMAX, bool EXACT>
 __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, int inverse, const float* __restrict__ x,
                                                                 int64_t ldx, const float* __restrict__ params,
                                                                 const int32_t* __restrict__ t_cols, int d_t,
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, 
     extern __shared__ __align__(16) float sp[];   // [kRowsThreads * M] staged parameters, then [kRowsThreads] lad
     // float4 per thread staged in registers = ceil(M_max / 4); register prefetch only for the common small bin counts
     constexpr int kMaxPrefetch = KMAX <= 16 ? (3 * KMAX + 1 + 3) / 4 : 1;
-    const int K = p.num_bins;
+    const int K = EXACT ? KMAX : p.num_bins;
     const int M = p.linear_tails ? 3 * K - 1 : 3 * K + 1;
     float* s_lad = sp + kRowsThreads * M;
     const int tid = threadIdx.x;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, 
                 for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? q[2 * K + k] : 0.0f;
             }
             float yy;
-            rqs_eval<KMAX>(p, inverse != 0, x[row * ldx + col], w, h, d, yy, ll, flag);
+            rqs_eval<KMAX, EXACT>(p, inverse != 0, x[row * ldx + col], w, h, d, yy, ll, flag);
             y[row * ldy + col] = yy;
         }
 
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, 
     if (flag && flags) atomicOr(flags, flag);
 }
 
-template <int KMAX>
+template <int KMAX, bool EXACT>
 static int launch_rows(const SplineParams& p, int inverse, const float* x, int64_t ldx, const float* params,
                        const int32_t* t_cols, int d_t, const int32_t* id_cols, int d_id, float* y, int64_t ldy,
                        float* lad_accum, int64_t n_rows, int32_t* flags, cudaStream_t st) {
@@ -242,13 +242,13 @@ static int launch_rows(const SplineParams& p, int inverse, const float* x, int64
     const int M = p.linear_tails ? 3 * K - 1 : 3 * K + 1;
     const size_t smem = (size_t)(kRowsThreads * M + kRowsThreads) * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(rqs_rows_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(rqs_rows_kernel<KMAX, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     const int rpg = d_t >= kRowsThreads ? 1 : max(1, kRowsThreads / d_t);
     const int64_t n_groups = (n_rows + rpg - 1) / rpg;
     const int grid = (int)std::min<int64_t>(n_groups, 148 * 32);
-    rqs_rows_kernel<KMAX><<<grid, kRowsThreads, smem, st>>>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy,
+    rqs_rows_kernel<KMAX, EXACT><<<grid, kRowsThreads, smem, st>>>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy,
                                                             lad_accum, n_rows, rpg, flags);
     return check_launch("rqs_rows_kernel");
 }
@@ -270,13 +270,15 @@ extern "C" int nfk_rqs_elementwise(const NfkSplineDesc* desc, int inverse, const
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = 256;
     const int grid = (int)std::min<int64_t>((n_elem + threads - 1) / threads, 148 * 64);
-#define NFK_LAUNCH_EW(KM)                                                                                             \
-    rqs_elementwise_kernel<KM><<<grid, threads, 0, st>>>(p, inverse, x, uw, uh, ud, stride_w, stride_h, stride_d,      \
-                                                         param_period, y, lad, n_elem, flags)
-    if (p.num_bins <= 8) NFK_LAUNCH_EW(8);
-    else if (p.num_bins <= 16) NFK_LAUNCH_EW(16);
-    else if (p.num_bins <= 32) NFK_LAUNCH_EW(32);
-    else NFK_LAUNCH_EW(64);
+#define NFK_LAUNCH_EW(KM, EX)                                                                                         \
+    rqs_elementwise_kernel<KM, EX><<<grid, threads, 0, st>>>(p, inverse, x, uw, uh, ud, stride_w, stride_h, stride_d,  \
+                                                             param_period, y, lad, n_elem, flags)
+    if (p.num_bins == 8) NFK_LAUNCH_EW(8, true);
+    else if (p.num_bins < 8) NFK_LAUNCH_EW(8, false);
+    else if (p.num_bins == 16) NFK_LAUNCH_EW(16, true);
+    else if (p.num_bins < 16) NFK_LAUNCH_EW(16, false);
+    else if (p.num_bins <= 32) NFK_LAUNCH_EW(32, false);
+    else NFK_LAUNCH_EW(64, false);
 #undef NFK_LAUNCH_EW
     return check_launch("rqs_elementwise_kernel");
 }
@@ -293,11 +295,13 @@ extern "C" int nfk_rqs_rows(const NfkSplineDesc* desc, int inverse, const float*
     NFK_REQUIRE(d_id == 0 || id_cols, "id_cols is NULL");
     NFK_REQUIRE(x != y, "y must not alias x");
     cudaStream_t st = (cudaStream_t)stream;
-    if (p.num_bins <= 8)
-        return launch_rows<8>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
-    if (p.num_bins <= 16)
-        return launch_rows<16>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
-    if (p.num_bins <= 32)
-        return launch_rows<32>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
-    return launch_rows<64>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st);
+#define NFK_ROWS(KM, EX) \
+    return launch_rows<KM, EX>(p, inverse, x, ldx, params, t_cols, d_t, id_cols, d_id, y, ldy, lad_accum, n_rows, flags, st)
+    if (p.num_bins == 8) NFK_ROWS(8, true);
+    if (p.num_bins < 8) NFK_ROWS(8, false);
+    if (p.num_bins == 16) NFK_ROWS(16, true);
+    if (p.num_bins < 16) NFK_ROWS(16, false);
+    if (p.num_bins <= 32) NFK_ROWS(32, false);
+    NFK_ROWS(64, false);
+#undef NFK_ROWS
 }

@@ -110,11 +110,12 @@ NFK_HD float fast_softplus(float x, float beta, float inv_beta) {
 // result inside the fp32 round-off of the reference: softmax as ex2((u - max) * log2e/sqrt(H)) (MUFU, rel. error
 // <= 2^-22) normalised by ONE reciprocal per softmax instead of K divisions; the bin ratio, theta and the rational
 // function keep IEEE divisions, logf/log1pf/expf of the two derivatives and of the log-determinant stay accurate.
-template <int KMAX>
+// EXACT: the caller guarantees p.num_bins == KMAX, which lets every `k < K` guard fold away at compile time.
+template <int KMAX, bool EXACT = false>
 NFK_HD void rqs_eval(const SplineParams& p, bool inverse, float x_in, const float (&uw)[KMAX],
                                          const float (&uh)[KMAX], const float (&ud)[KMAX + 1], float& y, float& lad,
                                          int& flag) {
-    const int K = p.num_bins;
+    const int K = EXACT ? KMAX : p.num_bins;
     const bool inside = (x_in >= p.left) && (x_in <= p.right);   // NaN -> outside (reference :26-39)
     if (!p.linear_tails && !inside) flag |= 1;                   // reference raises InputOutsideDomain (:81-82)
     const float x = inside ? x_in : (x_in > p.right ? p.right : p.left);
