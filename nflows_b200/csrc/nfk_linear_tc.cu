@@ -32,8 +32,6 @@
 namespace nfk {
 namespace tc {
 
-constexpr int LINEAR_SMEM_BYTES = SMEM_BYTES + 8 * 32 * 33 * 4;   // + one 32x33 transpose buffer per epilogue warp
-
 struct Params {
     const float* bias;       // [N] or null
     const float* residual;   // [n_rows, ldr] or null
@@ -158,8 +156,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
         const int half = (warp - 4) >> 2;         // column half of the tile
         int acc = 0; uint32_t acc_phase = 0;
-        float* stage = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256) + (warp - 4) * (32 * 33);   // 32x32 (+pad) per warp
+        const bool vec_y = p.y && (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const bool vec_s = p.y_hi && (p.lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y_hi) & 15) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.y_lo) & 15) == 0);
+        const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int64_t row = (int64_t)(t % p.num_m_tiles) * BM + q * 32 + lane;
             const int n0 = (t / p.num_m_tiles) * p.BN + half * HALF;
             float sum[HALF];
             for (int g = 0; g < num_groups; ++g) {
@@ -193,70 +195,65 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            // ---- tile epilogue.  A thread owns one ROW of the accumulator, but a row-per-thread global access touches 32
-            // different 128-byte lines per instruction (measured: the LSU, not the tensor pipe, bounded the 256-wide trunk
-            // layers).  Every 32x32 block therefore goes through a per-warp shared-memory transpose so that global loads
-            // and stores are issued with lanes = consecutive columns of one row (one full line per instruction).
-            const int64_t row_base = (int64_t)(t % p.num_m_tiles) * BM + q * 32;
+            if (row < p.n_rows) {
 #pragma unroll
-            for (int c = 0; c < HALF; c += 32) {
-                const int col0 = n0 + c;
-                if (c + half * HALF >= p.BN || col0 >= p.N) continue;        // warp-uniform
-                const bool col_ok = col0 + lane < p.N;
-                float v[32];
+                for (int c = 0; c < HALF; c += 16) {
+                    const int col0 = n0 + c;
+                    if (c + half * HALF >= p.BN || col0 >= p.N) continue;
+                    float v[16];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = sum[c + j];
-                    if (p.bias && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
-                    if (p.relu_out) x = fmaxf(x, 0.0f);
-                    v[j] = x;
-                }
-                if (p.residual) {
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const int64_t rr = row_base + r;
-                        stage[r * 33 + lane] = (rr < p.n_rows && col_ok) ? p.residual[rr * p.ldr + col0 + lane] : 0.0f;
+                    for (int j = 0; j < 16; ++j) {
+                        float x = sum[c + j];
+                        if (p.bias && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+                        if (p.relu_out) x = fmaxf(x, 0.0f);
+                        v[j] = x;
                     }
-                    __syncwarp();
+                    const bool full16 = col0 + 16 <= p.N;
+                    if (p.residual) {
+                        const float* rp = p.residual + row * p.ldr + col0;
+                        if (vec_r && full16) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += stage[lane * 33 + j];
-                    __syncwarp();
-                }
-                if (p.y) {
+                            for (int j = 0; j < 4; ++j) {
+                                float4 r4 = *reinterpret_cast<const float4*>(rp + 4 * j);
+                                v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+                            }
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
-                    __syncwarp();
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const int64_t rr = row_base + r;
-                        if (rr < p.n_rows && col_ok) p.y[rr * p.ldy + col0 + lane] = stage[r * 33 + lane];
+                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N) v[j] += rp[j];
+                        }
                     }
-                    __syncwarp();
-                }
-                if (p.y_hi) {
+                    if (p.y) {
+                        float* yp = p.y + row * p.ldy + col0;
+                        if (vec_y && full16) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float x = p.split_relu ? fmaxf(v[j], 0.0f) : v[j];
-                        const float h = tf32_hi(x);
-                        stage[lane * 33 + j] = h;
-                        v[j] = x - h;                                          // lo part, exact
-                    }
-                    __syncwarp();
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const int64_t rr = row_base + r;
-                        if (rr < p.n_rows && col_ok) p.y_hi[rr * p.lds + col0 + lane] = stage[r * 33 + lane];
-                    }
-                    __syncwarp();
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
-                    __syncwarp();
-#pragma unroll 8
-                    for (int r = 0; r < 32; ++r) {
-                        const int64_t rr = row_base + r;
-                        if (rr < p.n_rows && col_ok) p.y_lo[rr * p.lds + col0 + lane] = stage[r * 33 + lane];
+                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N) yp[j] = v[j];
+                        }
                     }
-                    __syncwarp();
+                    if (p.y_hi) {
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = p.split_relu ? fmaxf(v[j], 0.0f) : v[j];
+                            hi[j] = tf32_hi(x);
+                            lo[j] = x - hi[j];
+                        }
+                        float* hp = p.y_hi + row * p.lds + col0;
+                        float* lp = p.y_lo + row * p.lds + col0;
+                        if (vec_s && full16) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                *reinterpret_cast<float4*>(hp + 4 * j) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                                *reinterpret_cast<float4*>(lp + 4 * j) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N) { hp[j] = hi[j]; lp[j] = lo[j]; }
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -383,12 +380,12 @@ extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t l
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LINEAR_SMEM_BYTES);
-        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::LINEAR_SMEM_BYTES, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::SMEM_BYTES, cudaGetErrorString(e));
         attr_set = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = tiles < tc::sm_count() ? tiles : tc::sm_count();
-    tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::LINEAR_SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
     return check_launch("linear_tf32x3_kernel");
 }
