@@ -160,10 +160,42 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const bool vec_s = p.y_hi && (p.lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y_hi) & 15) == 0) &&
                            ((reinterpret_cast<uintptr_t>(p.y_lo) & 15) == 0);
         const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+        const bool vec_b = !p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int64_t row = (int64_t)(t % p.num_m_tiles) * BM + q * 32 + lane;
             const int n0 = (t / p.num_m_tiles) * p.BN + half * HALF;
+            // The running sums start from bias (+ residual when no relu sits between them): the loads are issued here, at the
+            // start of the tile, and complete under the first MMAs instead of stalling the tile epilogue (ncu: the serialised
+            // DRAM-latency residual reads of the epilogue held up drains -> MMA -> TMA; 15 % tensor activity on 256x256).
+            const bool fold_residual = p.residual && !p.relu_out;
             float sum[HALF];
+#pragma unroll
+            for (int c = 0; c < HALF; c += 4) {
+                const int col = n0 + c;
+                float4 init = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c + half * HALF < p.BN && col + 3 < p.N && vec_b) {
+                    if (p.bias) init = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    if (fold_residual && row < p.n_rows) {
+                        if (vec_r) {
+                            const float4 r4 = __ldcs(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
+                            init.x += r4.x; init.y += r4.y; init.z += r4.z; init.w += r4.w;
+                        } else {
+                            const float* rp = p.residual + row * p.ldr + col;
+                            init.x += rp[0]; init.y += rp[1]; init.z += rp[2]; init.w += rp[3];
+                        }
+                    }
+                } else if (c + half * HALF < p.BN) {
+                    float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (col + j < p.N) {
+                            if (p.bias) t4[j] = __ldg(p.bias + col + j);
+                            if (fold_residual && row < p.n_rows) t4[j] += p.residual[row * p.ldr + col + j];
+                        }
+                    init = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                }
+                sum[c] = init.x; sum[c + 1] = init.y; sum[c + 2] = init.z; sum[c + 3] = init.w;
+            }
             for (int g = 0; g < num_groups; ++g) {
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
@@ -176,17 +208,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     tmem_ld_wait();
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        if (g == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) sum[c + 32 * u + j] = __uint_as_float(raw[u][j]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 2) {              // packed fp32x2 round-to-nearest adds (FADD2)
-                                const float2 r2 = __fadd2_rn(make_float2(sum[c + 32 * u + j], sum[c + 32 * u + j + 1]),
-                                                             make_float2(__uint_as_float(raw[u][j]), __uint_as_float(raw[u][j + 1])));
-                                sum[c + 32 * u + j] = r2.x;
-                                sum[c + 32 * u + j + 1] = r2.y;
-                            }
+                        for (int j = 0; j < 32; j += 2) {                  // packed fp32x2 round-to-nearest adds (FADD2)
+                            const float2 r2 = __fadd2_rn(make_float2(sum[c + 32 * u + j], sum[c + 32 * u + j + 1]),
+                                                         make_float2(__uint_as_float(raw[u][j]), __uint_as_float(raw[u][j + 1])));
+                            sum[c + 32 * u + j] = r2.x;
+                            sum[c + 32 * u + j + 1] = r2.y;
                         }
                     }
                 }
@@ -203,13 +230,12 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float x = sum[c + j];
-                        if (p.bias && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
+                        float x = sum[c + j];                              // bias (and a foldable residual) already included
                         if (p.relu_out) x = fmaxf(x, 0.0f);
                         v[j] = x;
                     }
                     const bool full16 = col0 + 16 <= p.N;
-                    if (p.residual) {
+                    if (p.residual && !fold_residual) {
                         const float* rp = p.residual + row * p.ldr + col0;
                         if (vec_r && full16) {
 #pragma unroll
