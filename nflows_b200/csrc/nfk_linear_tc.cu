@@ -169,32 +169,41 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             // DRAM-latency residual reads of the epilogue held up drains -> MMA -> TMA; 15 % tensor activity on 256x256).
             const bool fold_residual = p.residual && !p.relu_out;
             float sum[HALF];
+            // pass 1: every residual load is issued before anything depends on one (in-order issue: a dependent add between
+            // two loads would serialise the DRAM latencies)
 #pragma unroll
             for (int c = 0; c < HALF; c += 4) {
                 const int col = n0 + c;
-                float4 init = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c + half * HALF < p.BN && col + 3 < p.N && vec_b) {
-                    if (p.bias) init = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                    if (fold_residual && row < p.n_rows) {
-                        if (vec_r) {
-                            const float4 r4 = __ldcs(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
-                            init.x += r4.x; init.y += r4.y; init.z += r4.z; init.w += r4.w;
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (fold_residual && row < p.n_rows && c + half * HALF < p.BN) {
+                    if (vec_r && col + 3 < p.N) {
+                        r4 = __ldcs(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
+                    } else {
+                        const float* rp = p.residual + row * p.ldr + col;
+                        if (col < p.N) r4.x = rp[0];
+                        if (col + 1 < p.N) r4.y = rp[1];
+                        if (col + 2 < p.N) r4.z = rp[2];
+                        if (col + 3 < p.N) r4.w = rp[3];
+                    }
+                }
+                sum[c] = r4.x; sum[c + 1] = r4.y; sum[c + 2] = r4.z; sum[c + 3] = r4.w;
+            }
+            // pass 2: bias (L1-resident broadcast loads)
+            if (p.bias) {
+#pragma unroll
+                for (int c = 0; c < HALF; c += 4) {
+                    const int col = n0 + c;
+                    if (c + half * HALF < p.BN) {
+                        if (vec_b && col + 3 < p.N) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                            sum[c] += b4.x; sum[c + 1] += b4.y; sum[c + 2] += b4.z; sum[c + 3] += b4.w;
                         } else {
-                            const float* rp = p.residual + row * p.ldr + col;
-                            init.x += rp[0]; init.y += rp[1]; init.z += rp[2]; init.w += rp[3];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (col + j < p.N) sum[c + j] += __ldg(p.bias + col + j);
                         }
                     }
-                } else if (c + half * HALF < p.BN) {
-                    float t4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (col + j < p.N) {
-                            if (p.bias) t4[j] = __ldg(p.bias + col + j);
-                            if (fold_residual && row < p.n_rows) t4[j] += p.residual[row * p.ldr + col + j];
-                        }
-                    init = make_float4(t4[0], t4[1], t4[2], t4[3]);
                 }
-                sum[c] = init.x; sum[c + 1] = init.y; sum[c + 2] = init.z; sum[c + 3] = init.w;
             }
             for (int g = 0; g < num_groups; ++g) {
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
