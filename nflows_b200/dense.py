@@ -90,7 +90,7 @@ def _run_trunk_block(chain, x, id_cols, use_tc, copy_identity_to, last_pair_out)
                 skip_src = y
             state = ChainState(raw=y, pair=pair)
         return state
-    hidden = K.gather_cols(x, id_cols)
+    hidden = x if id_cols is None else K.gather_cols(x, id_cols)
     branch = None
     for weight, bias, relu_in, relu_out, residual in body:
         b = bias.detach() if bias is not None else None

@@ -1,3 +1,5 @@
+from .autoregressive import (AutoregressiveTransform, MaskedAffineAutoregressiveTransform,
+                             MaskedPiecewiseRationalQuadraticAutoregressiveTransform)
 from .base import (CompositeTransform, InputOutsideDomain, InverseNotAvailable, InverseTransform,
                    MultiscaleCompositeTransform, Transform)
 from .coupling import (AdditiveCouplingTransform, AffineCouplingTransform, CouplingTransform,

@@ -272,6 +272,43 @@ def std_normal_log_prob(x):
     return -0.5 * torch.sum(x ** 2, dim=list(range(1, x.dim()))) - log_z
 
 
+def made(sd, p, x):
+    """transforms/made.py:17-283: MADE with residual blocks, relu, no context / BN / dropout; masks are stored buffers."""
+    lin = lambda q, t: F.linear(t, sd[q + "weight"] * sd[q + "mask"], sd[q + "bias"])
+    t = lin(p + "initial_layer.", x)
+    n = 0
+    while "{}blocks.{}.linear_layers.0.weight".format(p, n) in sd:
+        q = "{}blocks.{}.linear_layers.".format(p, n)
+        r = lin(q + "0.", F.relu(t))
+        r = lin(q + "1.", F.relu(r))
+        t = t + r
+        n += 1
+    return lin(p + "final_layer.", t)
+
+
+def ar_rq(sd, p, x, num_bins, tails=None, tail_bound=1.0, inverse=False):
+    """transforms/autoregressive.py:37-52 (forward = one MADE pass; inverse = D passes, keeping the last logabsdet) and
+    :453-495 (params viewed [B, D, M]; no 1/sqrt(H) rescale because transforms.made.MADE has no hidden_features)."""
+    net = p + "autoregressive_net."
+
+    def elementwise(inp, params, inv):
+        prm = params.view(inp.shape[0], inp.shape[1], -1)
+        uw, uh, ud = prm[..., :num_bins], prm[..., num_bins:2 * num_bins], prm[..., 2 * num_bins:]
+        if tails is None:
+            y, lad = rq_spline(inp, uw, uh, ud, inverse=inv)
+        else:
+            y, lad = rq_spline_unconstrained(inp, uw, uh, ud, inverse=inv, tails=tails, tail_bound=tail_bound)
+        return y, torch.sum(lad, dim=1)
+
+    if not inverse:
+        return elementwise(x, made(sd, net, x), False)
+    out = torch.zeros_like(x)
+    lad = None
+    for _ in range(x.shape[1]):
+        out, lad = elementwise(x, made(sd, net, out), True)
+    return out, lad
+
+
 # --------------------------------------------------------------------------------------------
 # composite / flow driven by a spec: list of (kind, prefix, kwargs)
 # --------------------------------------------------------------------------------------------
@@ -281,6 +318,7 @@ _KINDS = {
     "perm": permutation,
     "rq_coupling": rq_coupling,
     "affine_coupling": affine_coupling,
+    "ar_rq": ar_rq,
 }
 
 

@@ -225,6 +225,33 @@ def main():
     save("nsf784_full", dict(seed=0, perturb_seed=2, x=x, log_prob=lp, z=z, log_prob_fp64=lpd, checksum=ck,
                              features=784, hidden=256, layers=10))
 
+    # ---- g_ar_rq: BASELINE configs[3] shape -- MaskedPiecewiseRationalQuadraticAutoregressiveTransform D=64 H=256 K=8
+    # (weights by seed; final layer x30 so the splines are far from the identity), forward and the D-pass inverse
+    torch.manual_seed(0)
+    ar = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=64, hidden_features=256, num_bins=8,
+                                                                   tails="linear", tail_bound=3.0, num_blocks=2).eval()
+    for name, p in ar.named_parameters():
+        if "final_layer" in name:
+            p.mul_(30.0)
+    torch.manual_seed(1)
+    x = torch.randn(96, 64) * 1.3
+    y, lad = ar(x)
+    xi, li = ar.inverse(x)
+    yd, ladd = ar.double()(x.double())
+    save("ar_rq", dict(seed=0, final_scale=30.0, x=x, y=y, lad=lad, xinv=xi, ladinv=li, y_fp64=yd, lad_fp64=ladd,
+                       checksum=weight_checksum(ar.float().state_dict())))
+    # small variant with the weights stored, for the CPU oracle
+    torch.manual_seed(2)
+    ar = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=6, hidden_features=16, num_bins=4, tails=None,
+                                                                   num_blocks=1).eval()
+    for name, p in ar.named_parameters():
+        if "final_layer" in name:
+            p.mul_(20.0)
+    x = torch.rand(40, 6)
+    y, lad = ar(x)
+    xi, li = ar.inverse(x)
+    save("ar_rq_small", dict(sd=ar.state_dict(), x=x, y=y, lad=lad, xinv=xi, ladinv=li))
+
 
 if __name__ == "__main__":
     main()

@@ -118,3 +118,22 @@ def test_seeded_construction_matches_reference_weights():
     ck = float(sum(v.double().abs().sum() for v in flow.state_dict().values() if v.is_floating_point()))
     assert abs(ck - g["checksum"]) <= 1e-9 * abs(g["checksum"])
     assert rel_err(flow.log_prob(g["x"]), g["log_prob"]) <= TOL
+
+
+@torch.no_grad()
+def test_autoregressive_rq_cpu_seeded():
+    g = load_golden("ar_rq")
+    torch.manual_seed(g["seed"])
+    ar = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=64, hidden_features=256, num_bins=8, tails="linear",
+                                                                   tail_bound=3.0, num_blocks=2).eval()
+    for name, p in ar.named_parameters():
+        if "final_layer" in name:
+            p.mul_(g["final_scale"])
+    y, lad = ar(g["x"])
+    assert rel_err(y, g["y"]) <= TOL and rel_err(lad, g["lad"]) <= TOL
+    g2 = load_golden("ar_rq_small")
+    ar2 = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=6, hidden_features=16, num_bins=4, tails=None,
+                                                                    num_blocks=1).eval()
+    ar2.load_state_dict(g2["sd"])
+    xi, li = ar2.inverse(g2["x"])
+    assert rel_err(xi, g2["xinv"]) <= TOL and rel_err(li, g2["ladinv"]) <= TOL

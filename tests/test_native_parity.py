@@ -452,3 +452,38 @@ def test_next_rows_native_vs_torch_path(cuda_device):
         got = flow.to(cuda_device).log_prob(x.to(cuda_device))
     assert rel_err(got.cpu(), want) <= TOL
     assert flow.sample(9).shape == (9, 10)
+
+
+@torch.no_grad()
+def test_autoregressive_rq_transform_cfg4(cuda_device):
+    """BASELINE configs[3]: MaskedPiecewiseRationalQuadraticAutoregressiveTransform D=64 K=8 -- forward (one MADE pass on the
+    tensor-core dense chain + fused spline kernel) and the 64-pass inverse, against the reference's outputs."""
+    g = load_golden("ar_rq")
+    torch.manual_seed(g["seed"])
+    ar = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=64, hidden_features=256, num_bins=8, tails="linear",
+                                                                   tail_bound=3.0, num_blocks=2).eval()
+    for name, p in ar.named_parameters():
+        if "final_layer" in name:
+            p.mul_(g["final_scale"])
+    ck = float(sum(v.double().abs().sum() for v in ar.state_dict().values() if v.is_floating_point()))
+    if abs(ck - g["checksum"]) > 1e-9 * abs(g["checksum"]):
+        pytest.skip("torch CPU RNG stream differs from the fixture's")
+    ar = ar.to(cuda_device)
+    x = g["x"].to(cuda_device)
+    with native_launches():
+        y, lad = ar(x)
+    assert rel_err(y.cpu(), g["y_fp64"]) <= max(TOL, 3 * rel_err(g["y"], g["y_fp64"]))
+    assert rel_err(lad.cpu(), g["lad_fp64"]) <= max(3e-5, 3 * rel_err(g["lad"], g["lad_fp64"]))
+    before = _native.launch_count()
+    xi, li = ar.inverse(x)
+    assert _native.launch_count() - before >= 64          # one fused pass per feature
+    assert rel_err(xi.cpu(), g["xinv"]) <= 1e-4 and rel_err(li.cpu(), g["ladinv"]) <= 1e-3
+    back, lb = ar.inverse(y)
+    assert rel_err(back.cpu(), g["x"]) <= 1e-3
+    # FFMA / unfused route gives the same answer
+    config.fuse_coupling = False
+    try:
+        y2, lad2 = ar(x)
+    finally:
+        config.fuse_coupling = True
+    assert rel_err(y2, y) <= 2e-5

@@ -111,3 +111,11 @@ def test_nsf_small_flow():
                            g["noise"], inverse=True)
     assert rel_err(xs, g["sample"]) <= TOL and rel_err(lads, g["lad_inverse"]) <= TOL
     assert rel_err(O.flow_log_prob_chunked(g["sd"], spec, g["x"], chunk=100), g["log_prob"]) <= TOL
+
+
+def test_autoregressive_rq_small():
+    g = load_golden("ar_rq_small")
+    y, l = O.ar_rq(g["sd"], "", g["x"], num_bins=4, tails=None)
+    assert rel_err(y, g["y"]) <= TOL and rel_err(l, g["lad"]) <= TOL
+    xi, li = O.ar_rq(g["sd"], "", g["x"], num_bins=4, tails=None, inverse=True)
+    assert rel_err(xi, g["xinv"]) <= TOL and rel_err(li, g["ladinv"]) <= TOL

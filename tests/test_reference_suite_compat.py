@@ -17,7 +17,7 @@ REF = "/root/reference"
 FILES = ["tests/transforms/base_test.py", "tests/transforms/coupling_test.py", "tests/transforms/splines/rational_quadratic_test.py",
          "tests/transforms/normalization_test.py", "tests/transforms/lu_test.py", "tests/transforms/linear_test.py",
          "tests/transforms/permutations_test.py", "tests/transforms/standard_test.py", "tests/transforms/conv_test.py",
-         "tests/transforms/reshape_test.py", "tests/flows/base_test.py", "tests/flows/realnvp_test.py",
+         "tests/transforms/reshape_test.py", "tests/transforms/made_test.py", "tests/flows/base_test.py", "tests/flows/realnvp_test.py",
          "tests/distributions/normal_test.py", "tests/utils/torchutils_test.py"]
 DESELECT = ["tests/transforms/linear_test.py::NaiveLinearTest",     # O(D^3) slogdet linear: out of scope
             "tests/transforms/coupling_test.py::UMNNTransformTest"]  # third-party UMNN integrand: out of scope (row 14)
@@ -28,7 +28,7 @@ DROP_LINES = ["coupling.PiecewiseLinearCouplingTransform,", "coupling.PiecewiseQ
 
 ALIASES = ["transforms", "transforms.base", "transforms.coupling", "transforms.splines", "transforms.splines.rational_quadratic",
            "transforms.normalization", "transforms.linear", "transforms.lu", "transforms.permutations", "transforms.standard",
-           "transforms.conv", "transforms.reshape", "transforms.nonlinearities", "distributions", "distributions.base",
+           "transforms.conv", "transforms.reshape", "transforms.made", "transforms.autoregressive", "transforms.nonlinearities", "distributions", "distributions.base",
            "distributions.normal", "flows", "flows.base", "flows.realnvp", "nn", "nn.nets", "utils", "utils.torchutils",
            "utils.typechecks"]
 
