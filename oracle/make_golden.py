@@ -238,7 +238,9 @@ def main():
     y, lad = ar(x)
     xi, li = ar.inverse(x)
     yd, ladd = ar.double()(x.double())
+    xid, lid = ar.inverse(x.double())
     save("ar_rq", dict(seed=0, final_scale=30.0, x=x, y=y, lad=lad, xinv=xi, ladinv=li, y_fp64=yd, lad_fp64=ladd,
+                       xinv_fp64=xid, ladinv_fp64=lid,
                        checksum=weight_checksum(ar.float().state_dict())))
     # small variant with the weights stored, for the CPU oracle
     torch.manual_seed(2)
