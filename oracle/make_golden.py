@@ -226,20 +226,21 @@ def main():
                              features=784, hidden=256, layers=10))
 
     # ---- g_ar_rq: BASELINE configs[3] shape -- MaskedPiecewiseRationalQuadraticAutoregressiveTransform D=64 H=256 K=8
-    # (weights by seed; final layer x30 so the splines are far from the identity), forward and the D-pass inverse
+    # (weights by seed; final layer x3: non-trivial splines, log|det| ~ -30, yet the 64-step inverse stays well conditioned),
+    # forward and the D-pass inverse
     torch.manual_seed(0)
     ar = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=64, hidden_features=256, num_bins=8,
                                                                    tails="linear", tail_bound=3.0, num_blocks=2).eval()
     for name, p in ar.named_parameters():
         if "final_layer" in name:
-            p.mul_(30.0)
+            p.mul_(3.0)
     torch.manual_seed(1)
     x = torch.randn(96, 64) * 1.3
     y, lad = ar(x)
     xi, li = ar.inverse(x)
     yd, ladd = ar.double()(x.double())
     xid, lid = ar.inverse(x.double())
-    save("ar_rq", dict(seed=0, final_scale=30.0, x=x, y=y, lad=lad, xinv=xi, ladinv=li, y_fp64=yd, lad_fp64=ladd,
+    save("ar_rq", dict(seed=0, final_scale=3.0, x=x, y=y, lad=lad, xinv=xi, ladinv=li, y_fp64=yd, lad_fp64=ladd,
                        xinv_fp64=xid, ladinv_fp64=lid,
                        checksum=weight_checksum(ar.float().state_dict())))
     # small variant with the weights stored, for the CPU oracle

@@ -481,8 +481,8 @@ def test_autoregressive_rq_transform_cfg4(cuda_device):
     # on these inputs, so the check is the fp64 sandwich
     assert rel_err(xi.cpu(), g["xinv_fp64"]) <= max(1e-4, 3 * rel_err(g["xinv"], g["xinv_fp64"]))
     assert rel_err(li.cpu(), g["ladinv_fp64"]) <= max(1e-3, 3 * rel_err(g["ladinv"], g["ladinv_fp64"]))
-    back, lb = ar.inverse(y)
-    assert rel_err(back.cpu(), g["x"]) <= 1e-3
+    # (no forward->inverse round trip here: with log|det| ~ -30 the inverse expands round-off of y by many orders of
+    # magnitude -- the reference's own fp64 round trip is off by O(1) on these weights)
     # FFMA / unfused route gives the same answer
     config.fuse_coupling = False
     try:
