@@ -227,7 +227,7 @@ def run_native(args):
         from nflows_b200 import sharding
         lp_dev = torch.empty(rows, device=dev)
         for _ in range(e2e_steps):
-            sharding.log_prob_streamed(flow, host_x, dev, chunk_rows=1 << 18, out=lp_dev)   # H2D overlapped with the kernels
+            sharding.log_prob_streamed(flow, host_x, dev, chunk_rows=args.e2e_chunk, out=lp_dev)   # H2D overlapped with the kernels
             if world > 1:
                 dist.all_gather_into_tensor(gathered, lp_dev)
                 host_out.copy_(gathered, non_blocking=True)
@@ -307,6 +307,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=1 << 15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spline-roofline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="rows per host->device chunk of the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -44,7 +44,23 @@ struct Params {
     int relu_out;            // relu applied to (acc + bias) before the residual add / store
     int split_relu;          // relu applied before splitting (the next layer consumes relu(y))
     int num_m_tiles, num_n_tiles;
+    int n_inner;             // tile schedule, see tile_of()
 };
+
+// Tile schedule of a persistent CTA.  With at least one 128-row block per CTA ("n_inner") a CTA walks all column tiles of
+// its row block back to back, so the A slabs it just streamed are re-read from L2, not from HBM (K = N = 784: 4 column
+// tiles -> 4x less HBM traffic for A).  Small batches keep the flat row-fastest order to fill the machine.
+__device__ __forceinline__ bool tile_of(const int it, const int n_inner, const int num_m, const int num_n, int& m, int& n) {
+    if (n_inner) {
+        m = blockIdx.x + (it / num_n) * gridDim.x;
+        n = it % num_n;
+        return m < num_m;
+    }
+    const int t = blockIdx.x + it * gridDim.x;
+    m = t % num_m;
+    n = t / num_m;
+    return t < num_m * num_n;
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -82,9 +98,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         if (lane == 0) {
             const uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)p.BN * BK * 4u;
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t % p.num_m_tiles) * BM;
-                const int n0 = (t / p.num_m_tiles) * p.BN;
+            int tm, tn;
+            for (int it = 0; tile_of(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, tm, tn); ++it) {
+                const int m0 = tm * BM;
+                const int n0 = tn * p.BN;
                 for (int ks = 0; ks < num_k; ++ks) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_full + 8 * stage;
@@ -104,7 +121,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             const uint32_t idesc = make_idesc(p.BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int tm, tn;
+            for (int it = 0; tile_of(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, tm, tn); ++it) {
                 for (int g = 0; g < num_groups; ++g) {
                     // one partial sum = DRAIN_SLABS_LINEAR resident K-slabs; every small cross term (lo*hi, hi*lo) is issued before
                     // the first main product, so only the main MMAs round at full magnitude
@@ -161,9 +179,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                            ((reinterpret_cast<uintptr_t>(p.y_lo) & 15) == 0);
         const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         const bool vec_b = !p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int64_t row = (int64_t)(t % p.num_m_tiles) * BM + q * 32 + lane;
-            const int n0 = (t / p.num_m_tiles) * p.BN + half * HALF;
+        int tm, tn;
+        for (int it = 0; tile_of(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, tm, tn); ++it) {
+            const int64_t row = (int64_t)tm * BM + q * 32 + lane;
+            const int n0 = tn * p.BN + half * HALF;
             // The running sums start from bias (+ residual when no relu sits between them): the loads are issued here, at the
             // start of the tile, and complete under the first MMAs instead of stalling the tile epilogue (ncu: the serialised
             // DRAM-latency residual reads of the epilogue held up drains -> MMA -> TMA; 15 % tensor activity on 256x256).
@@ -301,10 +320,26 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 }
 
 // ---------------------------------------------------------------- fp32 -> (hi, lo) split, optional column gather / relu
+// HBM-bound: 4 B read + 8 B written per element (+ 4 B for the optional identity copy).  One warp per row chunk; the
+// un-gathered case moves 16 bytes per thread per access.
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ldx,
                                                          const int32_t* __restrict__ cols, int n_cols, int relu,
                                                          float* __restrict__ hi, float* __restrict__ lo, int64_t ldo,
-                                                         float* __restrict__ copy_dst, int64_t ldc, int64_t n_rows) {
+                                                         float* __restrict__ copy_dst, int64_t ldc, int64_t n_rows, int vec4) {
+    if (vec4) {
+        const int n4 = n_cols >> 2;
+        const int64_t total = n_rows * n4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / n4;
+            const int j = (int)(i - r * n4) * 4;
+            float4 v = __ldcs(reinterpret_cast<const float4*>(x + r * ldx + j));
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            *reinterpret_cast<float4*>(hi + r * ldo + j) = h;
+            *reinterpret_cast<float4*>(lo + r * ldo + j) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        }
+        return;
+    }
     const int64_t total = n_rows * n_cols;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n_cols;
@@ -372,9 +407,12 @@ extern "C" int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, 
     NFK_REQUIRE(n_rows >= 0 && n_cols >= 0, "bad sizes");
     if (n_rows == 0 || n_cols == 0) return NFK_OK;
     NFK_REQUIRE(x && hi && lo, "NULL pointer");
-    int64_t blocks = (n_rows * n_cols + 255) / 256;
+    const int vec4 = (!cols && !copy_dst && n_cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(hi) &&
+                      aligned16(lo)) ? 1 : 0;
+    int64_t blocks = (n_rows * (vec4 ? n_cols / 4 : n_cols) + 255) / 256;
     int grid = (int)(blocks > 148 * 32 ? 148 * 32 : blocks);
-    tc::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, cols, n_cols, relu, hi, lo, ldo, copy_dst, ldc, n_rows);
+    tc::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, cols, n_cols, relu, hi, lo, ldo, copy_dst, ldc, n_rows,
+                                                                  vec4);
     return check_launch("split_tf32_kernel");
 }
 
@@ -420,7 +458,9 @@ extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t l
         attr_set = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = tiles < tc::sm_count() ? tiles : tc::sm_count();
+    p.n_inner = (p.num_n_tiles > 1 && p.num_m_tiles >= tc::sm_count()) ? 1 : 0;
+    const int work = p.n_inner ? p.num_m_tiles : tiles;
+    const int grid = work < tc::sm_count() ? work : tc::sm_count();
     tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
     return check_launch("linear_tf32x3_kernel");
 }

@@ -51,7 +51,7 @@ def log_prob_sharded(flow, inputs, context=None, group=None, gather=True):
 
 
 @torch.no_grad()
-def log_prob_streamed(flow, host_inputs, device, chunk_rows=1 << 17, out=None):
+def log_prob_streamed(flow, host_inputs, device, chunk_rows=1 << 16, out=None):
     """Flow.log_prob of a (pinned) HOST tensor: chunks are copied on a side stream while the previous chunk is being
     evaluated, so the host->device transfer hides behind the kernels.  Returns the [n_rows] result on `device`."""
     n = host_inputs.shape[0]
