@@ -25,6 +25,8 @@
 //                                consumed by the next layer
 //   smem ring: 4 stages x (A_hi, A_lo, W_hi, W_lo) of K = 16 = 4 x 48 KB (three loads in flight while one slab is
 //   consumed: the 2 x 96 KB ring of the first version was latency-bound);  TMEM: 2 partial accumulators x 256 columns.
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "tc_common.cuh"
@@ -50,18 +52,26 @@ struct Params {
 // Tile schedule of a persistent CTA.  With at least one 128-row block per CTA ("n_inner") a CTA walks all column tiles of
 // its row block back to back, so the A slabs it just streamed are re-read from L2, not from HBM (K = N = 784: 4 column
 // tiles -> 4x less HBM traffic for A).  Small batches keep the flat row-fastest order to fill the machine.
-__device__ __forceinline__ bool tile_of(const int it, const int n_inner, const int num_m, const int num_n, int& m, int& n) {
+// With CL = 2 the two CTAs of a cluster take neighbouring row blocks (2u, 2u+1) of the SAME column tile and multicast
+// half of every weight slab to each other; a trailing odd row block is paired with an out-of-range one (all-zero A, no stores).
+template <int CL>
+__device__ __forceinline__ bool tile_of(const int it, const int n_inner, const int num_m, const int num_n, const int rank,
+                                        int& m, int& n) {
+    const int units = (num_m + CL - 1) / CL;                  // row-block groups
+    const int first = blockIdx.x / CL, step = gridDim.x / CL;
     if (n_inner) {
-        m = blockIdx.x + (it / num_n) * gridDim.x;
+        const int u = first + (it / num_n) * step;
+        m = u * CL + rank;
         n = it % num_n;
-        return m < num_m;
+        return u < units;
     }
-    const int t = blockIdx.x + it * gridDim.x;
-    m = t % num_m;
-    n = t / num_m;
-    return t < num_m * num_n;
+    const int t = first + it * step;
+    m = (t % units) * CL + rank;
+    n = t / units;
+    return t < units * num_n;
 }
 
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -79,16 +89,18 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     const int num_k = (p.K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
     const int num_groups = (num_k + DRAIN_SLABS_LINEAR - 1) / DRAIN_SLABS_LINEAR;     // partial sums per tile
 
     if (warp < 4) {
@@ -99,18 +111,26 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             const uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)p.BN * BK * 4u;
             int stage = 0; uint32_t phase = 0;
             int tm, tn;
-            for (int it = 0; tile_of(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, tm, tn); ++it) {
+            const int wrows = p.BN / CL;                                   // weight rows this CTA fetches per slab
+            for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
                 const int m0 = tm * BM;
                 const int n0 = tn * p.BN;
                 for (int ks = 0; ks < num_k; ++ks) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);           // every CTA of the cluster has released the slot
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     mbar_expect_tx(full, tx_bytes);
                     tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
                     tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
-                    tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n0);
-                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n0);
+                    if (CL == 1) {
+                        tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n0);
+                        tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n0);
+                    } else {
+                        const uint32_t off = (uint32_t)(cta_rank * wrows) * ROW_BYTES;
+                        tma_load_2d_multicast(sa + 2 * A_BYTES + off, &map_w_hi, full, ks * BK, n0 + cta_rank * wrows, cl_mask);
+                        tma_load_2d_multicast(sa + 2 * A_BYTES + B_BYTES + off, &map_w_lo, full, ks * BK, n0 + cta_rank * wrows,
+                                              cl_mask);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -122,7 +142,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int tm, tn;
-            for (int it = 0; tile_of(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, tm, tn); ++it) {
+            for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
                 for (int g = 0; g < num_groups; ++g) {
                     // one partial sum = DRAIN_SLABS_LINEAR resident K-slabs; every small cross term (lo*hi, hi*lo) is issued before
                     // the first main product, so only the main MMAs round at full magnitude
@@ -158,7 +178,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                                 const uint64_t adv = (uint64_t)(kk * 2);
                                 umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                             }
-                            umma_commit(bar_empty + 8 * stage);            // frees the smem slot when the MMAs retire
+                            if (CL == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot when the MMAs retire
+                            else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // ... in every CTA of the cluster
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -180,7 +201,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         const bool vec_b = !p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         int tm, tn;
-        for (int it = 0; tile_of(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, tm, tn); ++it) {
+        for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
             const int64_t row = (int64_t)tm * BM + q * 32 + lane;
             const int n0 = tn * p.BN + half * HALF;
             // The running sums start from bias (+ residual when no relu sits between them): the loads are issued here, at the
@@ -315,7 +336,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA exits while a peer may still signal its barriers
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
@@ -444,23 +465,43 @@ extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t l
     p.num_n_tiles = (out_features + bn - 1) / bn;
     p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
 
+    static int cluster_pref = 0;
+    if (!cluster_pref) {
+        const char* e = getenv("NFK_CLUSTER");
+        cluster_pref = (e && e[0] == '1') ? 1 : 2;
+    }
+    const int CL = (cluster_pref == 2 && p.num_m_tiles >= 2) ? 2 : 1;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     int rc;
     if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, in_features, lda, tc::BM))) return rc;
     if ((rc = tc::make_map(&ma_lo, a_lo, n_rows, in_features, lda, tc::BM))) return rc;
-    if ((rc = tc::make_map(&mw_hi, w_hi, out_features, in_features, ldw, bn))) return rc;
-    if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn))) return rc;
+    if ((rc = tc::make_map(&mw_hi, w_hi, out_features, in_features, ldw, bn / CL))) return rc;
+    if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn / CL))) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::SMEM_BYTES, cudaGetErrorString(e));
         attr_set = true;
     }
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    p.n_inner = (p.num_n_tiles > 1 && p.num_m_tiles >= tc::sm_count()) ? 1 : 0;
-    const int work = p.n_inner ? p.num_m_tiles : tiles;
-    const int grid = work < tc::sm_count() ? work : tc::sm_count();
-    tc::linear_tf32x3_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, p);
+    const int units = (p.num_m_tiles + CL - 1) / CL;
+    p.n_inner = 0;   // measured r1: walking the column tiles of a row block back to back did not help (L2-feed-, not HBM-bound)
+    const int work = units * p.num_n_tiles;
+    const int max_clusters = tc::sm_count() / CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CL * (work < max_clusters ? work : max_clusters)));
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, p)
+                               : cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    if (le != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(linear_tf32x3_kernel, cluster %d): %s", CL, cudaGetErrorString(le));
     return check_launch("linear_tf32x3_kernel");
 }
