@@ -112,29 +112,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             int stage = 0; uint32_t phase = 0;
             int tm, tn;
             const int wrows = p.BN / CL;                                   // weight rows this CTA fetches per slab
-            constexpr int PF = 12;                                         // A slabs prefetched into L2 ahead of the ring
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
                 const int m0 = tm * BM;
                 const int n0 = tn * p.BN;
-                int nm, nn;
-                const bool has_next = tile_of<CL>(it + 1, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, nm, nn);
-                if (it == 0) {
-                    for (int ks = 0; ks < min(PF, num_k); ++ks) {
-                        tma_prefetch_2d(&map_a_hi, ks * BK, m0);
-                        tma_prefetch_2d(&map_a_lo, ks * BK, m0);
-                    }
-                }
                 for (int ks = 0; ks < num_k; ++ks) {
-                    {   // keep the A stream PF slabs ahead (into the next tile of this CTA when this one runs out)
-                        const int pk = ks + PF;
-                        if (pk < num_k) {
-                            tma_prefetch_2d(&map_a_hi, pk * BK, m0);
-                            tma_prefetch_2d(&map_a_lo, pk * BK, m0);
-                        } else if (has_next && pk - num_k < num_k) {
-                            tma_prefetch_2d(&map_a_hi, (pk - num_k) * BK, nm * BM);
-                            tma_prefetch_2d(&map_a_lo, (pk - num_k) * BK, nm * BM);
-                        }
-                    }
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);           // every CTA of the cluster has released the slot
                     const uint32_t full = bar_full + 8 * stage;
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
