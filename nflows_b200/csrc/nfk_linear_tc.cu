@@ -136,8 +136,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
             }
         }
     } else if (warp == 1) {
-        // ================================================= MMA issuer (one thread)
-        if (lane == 0) {
+        // ================================================= MMA issuer.  The whole warp runs the loop (so stage indices and
+        // shared-memory descriptors stay in uniform registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
+        {
+            const bool leader = lane == 0;
             const uint32_t idesc = make_idesc(p.BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -165,8 +167,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 #pragma unroll
                             for (int kk = 0; kk < BK / 8; ++kk) {          // UMMA K = 8 tf32 = 32 bytes = +2 in descriptor units
                                 const uint64_t adv = (uint64_t)(kk * 2);
-                                umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
-                                umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                                if (leader) umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
+                                if (leader) umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                             }
                             if (++st == STAGES) st = 0;
                         }
@@ -176,14 +178,14 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
 #pragma unroll
                             for (int kk = 0; kk < BK / 8; ++kk) {
                                 const uint64_t adv = (uint64_t)(kk * 2);
-                                umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                                if (leader) umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                             }
-                            if (CL == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot when the MMAs retire
+                            if (!leader) {} else if (CL == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot when the MMAs retire
                             else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // ... in every CTA of the cluster
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
-                    umma_commit(bar_tfull + 8 * acc);                      // partial sum complete -> drain
+                    if (leader) umma_commit(bar_tfull + 8 * acc);                      // partial sum complete -> drain
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }

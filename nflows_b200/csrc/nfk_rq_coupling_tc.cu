@@ -34,14 +34,29 @@ struct FusedParams {
     SplineParams sp;
 };
 
+// Epilogue warpgroups of the fused kernel (compile-time).  Measured on B200, cfg 3 (ms per step spent in this kernel):
+// EWG = 2 (5 features per thread, BN = 240, 40 N-tiles): 263;  EWG = 4 (2 features per thread, BN = 192, 49 N-tiles): 274 --
+// the epilogue is not what the tensor pipe waits for, and narrower tiles re-stream the activations more often.
+#ifndef NFK_FUSED_EWG
+#define NFK_FUSED_EWG 2
+#endif
+constexpr int EWG = NFK_FUSED_EWG;
+constexpr int FUSED_THREADS = 128 + 128 * EWG;
+// registers: the launch allocates floor(64K / threads) per thread; the control warpgroup shrinks to 40 and the epilogue
+// warpgroups share what that frees (setmaxnreg needs multiples of 8)
+constexpr int FUSED_LAUNCH_REGS = (65536 / FUSED_THREADS) / 8 * 8 > 255 ? 248 : (65536 / FUSED_THREADS) / 8 * 8;
+constexpr int FUSED_EPI_REGS = ((FUSED_THREADS * FUSED_LAUNCH_REGS - 128 * 40) / (128 * EWG)) / 8 * 8;
+
 template <int NB, bool TAILS>
 struct FusedCfg {
     static constexpr int M = TAILS ? 3 * NB - 1 : 3 * NB + 1;   // parameters per feature
     static constexpr int MP = (M + 7) / 8 * 8;                  // padded
-    static constexpr int FPT = 128 / MP;                        // features per thread per tile
-    static constexpr int HALF_COLS = FPT * MP;                  // columns per accumulate/epilogue warp
-    static constexpr int BN = 2 * HALF_COLS;                    // tile columns (multiple of 16, <= 256)
-    static_assert(FPT >= 1 && BN <= BN_MAX && BN % 16 == 0, "unsupported bin count for the fused kernel");
+    static constexpr int FPT = BN_MAX / (EWG * MP);             // features per thread per tile
+    static constexpr int HALF_COLS = FPT * MP;                  // columns per accumulate/epilogue thread
+    static constexpr int TILE_FEATURES = EWG * FPT;
+    static constexpr int TILE_COLS = EWG * HALF_COLS;           // packed weight rows per tile
+    static constexpr int BN = (TILE_COLS + 15) / 16 * 16;       // MMA N (the pad columns compute the next feature's first rows, unused)
+    static_assert(FPT >= 1 && BN <= BN_MAX, "unsupported bin count for the fused kernel");
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -165,38 +180,49 @@ __device__ __forceinline__ void rqs_eval_multi(const SplineParams& p, bool inver
     }
 }
 
-// CL = CTAs per cluster.  With CL = 2 the two CTAs of a cluster work on neighbouring 128-row blocks and walk the same
-// sequence of weight tiles in lockstep: each loads HALF of every weight slab and multicasts it into both CTAs' shared
-// memory (cp.async.bulk.tensor ... .multicast::cluster), which halves the L2 -> SM weight stream -- the limiter of this
-// kernel (ncu: L2->SM 8.2 TB/s at 40 % tensor-pipe activity with CL = 1).
-template <int NB, bool TAILS, int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+// MODE 1: one CTA per 128-row block.
+// MODE 2: clusters of two CTAs on neighbouring 128-row blocks walking the same weight tiles in lockstep; each loads HALF of
+//         every weight slab and multicasts it into both CTAs' shared memory (halves the L2 -> SM weight stream; ncu: L2->SM
+//         8.2 TB/s at 40 % tensor-pipe activity in MODE 1, 57 % in MODE 2).
+// MODE 3: the same two CTAs as a tcgen05 CTA PAIR (cta_group::2): the leader issues ONE 256 x BN x 8 MMA for both SMs, each
+//         CTA keeps only its half of the weight tile (no multicast copy), so shared-memory operand reads per SM drop from
+//         (128 + BN) to (128 + BN/2) rows per MMA and the stage ring deepens from 4 to 6 slabs in the same 192 KB.
+template <int NB, bool TAILS, int MODE>
+__global__ void __launch_bounds__(FUSED_THREADS, 1)
 rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                          const FusedParams p) {
     using Cfg = FusedCfg<NB, TAILS>;
-    constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HALF_COLS, BN = Cfg::BN;
+    constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HALF_COLS, BN = Cfg::BN, TILE = Cfg::TILE_COLS;
+    constexpr bool PAIR = MODE == 3;
+    constexpr int CL = MODE == 1 ? 1 : 2;
+    constexpr int NST = PAIR ? PAIR_STAGES : STAGES;                 // slabs in the shared-memory ring
+    constexpr int SB = PAIR ? PAIR_STAGE_BYTES : STAGE_BYTES;        // bytes per slab: [A hi | A lo | W hi | W lo]
+    constexpr int WLO = 2 * A_BYTES + (PAIR ? B_BYTES / 2 : B_BYTES);   // offset of the W lo part inside a slab
+    static_assert(NST * SB <= STAGES * STAGE_BYTES, "ring must fit the launch's dynamic shared memory");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
-    const uint32_t bar_tfull = bars + 16 * STAGES, bar_tempty = bars + 16 * STAGES + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
-    float* s_lad = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);       // [128] half-1 partial log|det|
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * NST;
+    const uint32_t bar_tfull = bars + 16 * NST, bar_tempty = bars + 16 * NST + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * NST + 32);
+    float* s_lad = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);       // [EWG-1][128] partial log|det|
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (p.K + BK - 1) / BK;
     const int num_groups = (num_k + DRAIN_SLABS_FUSED - 1) / DRAIN_SLABS_FUSED;     // partial sums per tile
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        // MODE 2: both CTAs' MMA threads release a slot (the peer multicasts into it); MODE 3: the leader's commit reaches
+        // both CTAs' barriers, and the leader's accumulator barrier collects the epilogue warps of BOTH CTAs
+        for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, MODE == 2 ? 2 : 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * 4 * EWG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
     tc_fence_before();
     if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' barriers are initialised before anyone signals them
     tc_fence_after();
@@ -211,7 +237,9 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         if (warp == 0) {
             // ================================================= TMA producer
             if (lane == 0) {
-                constexpr uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)BN * BK * 4u;   // bytes landing in THIS CTA's stage
+                // bytes counted on the slab's barrier: MODE 1/2 everything landing in THIS CTA's slab; MODE 3 both CTAs' loads
+                // (A of both + both halves of W) on the leader's barrier
+                constexpr uint32_t tx_bytes = PAIR ? 2u * (2u * A_BYTES + (uint32_t)BN * BK * 4u) : 2u * A_BYTES + 2u * (uint32_t)BN * BK * 4u;
                 constexpr int WROWS = BN / CL;                                             // weight rows this CTA fetches
                 int stage = 0; uint32_t phase = 0;
                 for (int mb = first_block; mb < num_blocks; mb += block_step) {
@@ -220,73 +248,94 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                         for (int ks = 0; ks < num_k; ++ks) {
                             mbar_wait(bar_empty + 8 * stage, phase ^ 1);      // every CTA of the cluster has released the slot
                             const uint32_t full = bar_full + 8 * stage;
-                            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                            const uint32_t sa = smem_base + stage * SB;
+                            if (PAIR) {
+                                const uint32_t lead = mapa_rank(full, 0);
+                                if (cta_rank == 0) mbar_expect_tx(full, tx_bytes);
+                                tma_load_2d_pair(sa, &map_a_hi, lead, ks * BK, m * BM);
+                                tma_load_2d_pair(sa + A_BYTES, &map_a_lo, lead, ks * BK, m * BM);
+                                tma_load_2d_pair(sa + 2 * A_BYTES, &map_w_hi, lead, ks * BK, n * TILE + cta_rank * WROWS);
+                                tma_load_2d_pair(sa + WLO, &map_w_lo, lead, ks * BK, n * TILE + cta_rank * WROWS);
+                                if (++stage == NST) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             mbar_expect_tx(full, tx_bytes);
                             tma_load_2d(sa, &map_a_hi, full, ks * BK, m * BM);
                             tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m * BM);
                             if (CL == 1) {
-                                tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n * BN);
-                                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n * BN);
+                                tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n * TILE);
+                                tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n * TILE);
                             } else {
                                 const uint32_t off = (uint32_t)cta_rank * WROWS * ROW_BYTES;
-                                tma_load_2d_multicast(sa + 2 * A_BYTES + off, &map_w_hi, full, ks * BK, n * BN + cta_rank * WROWS, cl_mask);
+                                tma_load_2d_multicast(sa + 2 * A_BYTES + off, &map_w_hi, full, ks * BK, n * TILE + cta_rank * WROWS, cl_mask);
                                 tma_load_2d_multicast(sa + 2 * A_BYTES + B_BYTES + off, &map_w_lo, full, ks * BK,
-                                                      n * BN + cta_rank * WROWS, cl_mask);
+                                                      n * TILE + cta_rank * WROWS, cl_mask);
                             }
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            if (++stage == NST) { stage = 0; phase ^= 1; }
                         }
                     }
                 }
             }
-        } else if (warp == 1) {
-            // ================================================= MMA issuer (one thread): one partial sum per DRAIN_SLABS_FUSED slabs
-            if (lane == 0) {
-                const uint32_t idesc = make_idesc(BN);
+        } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
+            // ================================================= MMA issuer: one partial sum per DRAIN_SLABS_FUSED slabs.  The whole warp
+            // runs the loop (stage indices / descriptors stay uniform); only lane 0 issues tcgen05.mma / tcgen05.commit.
+            {
+                const bool leader = lane == 0;
+                const uint32_t idesc = make_idesc(BN, PAIR ? 2 * BM : BM);
                 int stage = 0; uint32_t phase = 0;
                 int acc = 0; uint32_t acc_phase = 0;
+                auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+                    if (!leader) return;
+                    if (PAIR) umma_tf32_pair(d, a, b, idesc, accumulate); else umma_tf32(d, a, b, idesc, accumulate);
+                };
                 for (int mb = first_block; mb < num_blocks; mb += block_step) {
                     for (int n = 0; n < p.num_n_tiles; ++n) {
                         for (int g = 0; g < num_groups; ++g) {
                             // one partial sum = DRAIN_SLABS_FUSED resident K-slabs; every small cross term (lo*hi, hi*lo) is
                             // issued before the first main product, so only the main MMAs round at full magnitude
                             const int slabs = min(DRAIN_SLABS_FUSED, num_k - g * DRAIN_SLABS_FUSED);
-                            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                            if (PAIR) mbar_wait_cluster(bar_tempty + 8 * acc, acc_phase ^ 1);
+                            else mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                             for (int j0 = 0; j0 < slabs; j0 += 2) {           // pairs of resident slabs: cross terms of both, then mains
                                 const int pair = min(2, slabs - j0);
                                 int st = stage; uint32_t ph = phase;
                                 for (int j = 0; j < pair; ++j) {
                                     mbar_wait(bar_full + 8 * st, ph);
-                                    if (++st == STAGES) { st = 0; ph ^= 1; }
+                                    if (++st == NST) { st = 0; ph ^= 1; }
                                 }
                                 tc_fence_after();
                                 st = stage;
                                 for (int j = 0; j < pair; ++j) {
-                                    const uint32_t sa = smem_base + st * STAGE_BYTES;
+                                    const uint32_t sa = smem_base + st * SB;
                                     const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
-                                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+                                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + WLO);
 #pragma unroll
                                     for (int kk = 0; kk < BK / 8; ++kk) {
                                         const uint64_t adv = (uint64_t)(kk * 2);
-                                        umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
-                                        umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                                        mma(d_tmem, a_lo + adv, w_hi + adv, (j0 | j | kk) != 0);
+                                        mma(d_tmem, a_hi + adv, w_lo + adv, 1);
                                     }
-                                    if (++st == STAGES) st = 0;
+                                    if (++st == NST) st = 0;
                                 }
                                 for (int j = 0; j < pair; ++j) {
-                                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                                    const uint32_t sa = smem_base + stage * SB;
                                     const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
 #pragma unroll
                                     for (int kk = 0; kk < BK / 8; ++kk) {
                                         const uint64_t adv = (uint64_t)(kk * 2);
-                                        umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                                        mma(d_tmem, a_hi + adv, w_hi + adv, 1);
                                     }
-                                    if (CL == 1) umma_commit(bar_empty + 8 * stage);
-                                    else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // releases the slot in every CTA
-                                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                    if (!leader) {}
+                                    else if (MODE == 1) umma_commit(bar_empty + 8 * stage);
+                                    else if (MODE == 2) umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // releases the slot in every CTA
+                                    else umma_commit_pair(bar_empty + 8 * stage, cl_mask);
+                                    if (++stage == NST) { stage = 0; phase ^= 1; }
                                 }
                             }
-                            umma_commit(bar_tfull + 8 * acc);
+                            if (!leader) {}
+                            else if (PAIR) umma_commit_pair(bar_tfull + 8 * acc, cl_mask);   // both CTAs' halves of the sum are complete
+                            else umma_commit(bar_tfull + 8 * acc);
                             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         }
                     }
@@ -294,10 +343,10 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-        // ================================================= accumulate + spline epilogue: 8 warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FUSED_EPI_REGS) : "memory");
+        // ================================================= accumulate + spline epilogue: 4 * EWG warps
         const int q = warp & 3;                   // TMEM lane quarter
-        const int half = (warp - 4) >> 2;         // which FPT features of the tile
+        const int half = (warp - 4) >> 2;         // warpgroup: which FPT features of the tile
         int acc = 0; uint32_t acc_phase = 0;
         int flag = 0;
         for (int mb = first_block; mb < num_blocks; mb += block_step) {
@@ -306,7 +355,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             const bool row_ok = row < p.n_rows;
             float lad_row = 0.0f;
             for (int n = 0; n < p.num_n_tiles; ++n) {
-                const int j0 = (n * 2 + half) * FPT;                       // first feature this thread owns in this tile
+                const int j0 = (n * EWG + half) * FPT;                     // first feature this thread owns in this tile
                 float xin[FPT];
                 int col[FPT];
 #pragma unroll
@@ -315,14 +364,14 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     col[f] = ok ? __ldg(p.t_cols + j0 + f) : 0;
                     xin[f] = ok ? __ldg(p.x + row * p.ldx + col[f]) : 0.0f;
                 }
-                // running sums start from the packed bias of this thread's columns (padded to whole tiles by the host); all
-                // loads are issued back-to-back here -- a load/add pair per column inside the first drain serialised 120
-                // L1 latencies per tile (ncu: 37 % of the epilogue warps' samples)
-                const float4* bias_tile = reinterpret_cast<const float4*>(p.bias + (int64_t)n * BN + half * HC);
+                // running sums start from the packed bias of this thread's columns; all loads are issued back-to-back here -- a
+                // load/add pair per column inside the first drain serialised 120 L1 latencies per tile (ncu: 37 % of the
+                // epilogue warps' samples)
+                const float4* bias_tile = reinterpret_cast<const float4*>(p.bias + (int64_t)j0 * MP);
                 float sum[HC];
 #pragma unroll
                 for (int c = 0; c < HC; c += 4) {
-                    const float4 b4 = __ldg(bias_tile + (c >> 2));
+                    const float4 b4 = (j0 + c / MP < p.d_t) ? __ldg(bias_tile + (c >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     sum[c] = b4.x; sum[c + 1] = b4.y; sum[c + 2] = b4.z; sum[c + 3] = b4.w;
                 }
                 for (int ks = 0; ks < num_groups; ++ks) {
@@ -330,14 +379,16 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HC;
 #pragma unroll
-                    for (int c = 0; c < HC; c += 40) {             // 5 TMEM loads in flight per wait
-                        uint32_t raw[5][8];
+                    constexpr int LDB = HC <= 48 ? 3 : 5;           // TMEM loads in flight per wait (register budget)
 #pragma unroll
-                        for (int u = 0; u < 5; ++u)
+                    for (int c = 0; c < HC; c += 8 * LDB) {
+                        uint32_t raw[LDB][8];
+#pragma unroll
+                        for (int u = 0; u < LDB; ++u)
                             if (c + 8 * u < HC) tmem_ld8(taddr + c + 8 * u, raw[u]);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int u = 0; u < 5; ++u)
+                        for (int u = 0; u < LDB; ++u)
                             if (c + 8 * u < HC) {
 #pragma unroll
                                 for (int i = 0; i < 8; i += 2) {       // packed fp32x2 round-to-nearest adds (FADD2)
@@ -350,7 +401,10 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * acc, 0));   // the leader's MMA thread reuses the accumulator
+                        else mbar_arrive(bar_tempty + 8 * acc);
+                    }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
                 // ---- spline on the FPT features held in registers, all features advanced together (ILP = FPT)
@@ -367,12 +421,17 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 }
                 __syncwarp();
             }
-            // ---- finish the row block: lad_accum[row] += (half 0 partial) + (half 1 partial), fixed order
+            // ---- finish the row block: lad_accum[row] += the warpgroups' partial sums, fixed order
             if (p.lad_accum) {
-                if (half == 1) s_lad[q * 32 + lane] = lad_row;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0 && row_ok) p.lad_accum[row] += lad_row + s_lad[q * 32 + lane];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half > 0) s_lad[(half - 1) * 128 + q * 32 + lane] = lad_row;
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * EWG) : "memory");
+                if (half == 0 && row_ok) {
+                    float t = lad_row;
+#pragma unroll
+                    for (int h = 1; h < EWG; ++h) t += s_lad[(h - 1) * 128 + q * 32 + lane];
+                    p.lad_accum[row] += t;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * EWG) : "memory");
             }
         }
         if (flag && p.flags) atomicOr(p.flags, flag);
@@ -380,32 +439,36 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 
     tc_fence_before();
     if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA exits while a peer may still signal its barriers
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
-static int cluster_size() {
-    static int cl = 0;
-    if (!cl) {
+// NFK_CLUSTER = 1: single CTAs, 3: CTA pairs (cta_group::2), anything else / unset: multicast clusters.  Measured (ms per
+// step in this kernel, cfg 3): mode 2 263, mode 3 288 -- with the GPU at its power cap (sw_power_cap, ~1.78 GHz) the pair's
+// lock-step accumulator hand-off costs more than the halved shared-memory operand traffic returns.
+static int cluster_mode() {
+    static int mode = 0;
+    if (!mode) {
         const char* e = getenv("NFK_CLUSTER");
-        cl = (e && e[0] == '1') ? 1 : 2;
+        mode = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;
     }
-    return cl;
+    return mode;
 }
 
-template <int NB, bool TAILS, int CL>
+template <int NB, bool TAILS, int MODE>
 static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo, int64_t ldw,
                            FusedParams& p, cudaStream_t st) {
     using Cfg = FusedCfg<NB, TAILS>;
+    constexpr int CL = MODE == 1 ? 1 : 2;
     const int packed_rows = p.d_t * Cfg::MP;
     CUtensorMap mw_hi, mw_lo;
     int rc;
     if ((rc = make_map(&mw_hi, w_hi, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
     if ((rc = make_map(&mw_lo, w_lo, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
-    p.num_n_tiles = (p.d_t + 2 * Cfg::FPT - 1) / (2 * Cfg::FPT);
-    constexpr int smem = SMEM_BYTES + 512;
+    p.num_n_tiles = (p.d_t + Cfg::TILE_FEATURES - 1) / Cfg::TILE_FEATURES;
+    constexpr int smem = SMEM_BYTES + 512 * EWG;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
         attr_set = true;
     }
@@ -413,7 +476,7 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     const int max_clusters = sm_count() / CL;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(CL * (blocks < max_clusters ? blocks : max_clusters)));
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(FUSED_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -421,7 +484,7 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, CL>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, MODE>, ma_hi, ma_lo, mw_hi, mw_lo, p);
     if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(rq_coupling_final_kernel, cluster %d): %s", CL, cudaGetErrorString(e));
     return check_launch("rq_coupling_final_kernel");
 }
@@ -429,8 +492,11 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
 template <int NB, bool TAILS>
 static int launch_fused(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo, int64_t ldw,
                         FusedParams& p, cudaStream_t st) {
-    return cluster_size() == 2 ? launch_fused_cl<NB, TAILS, 2>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st)
-                               : launch_fused_cl<NB, TAILS, 1>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+    switch (cluster_mode()) {
+        case 1: return launch_fused_cl<NB, TAILS, 1>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+        case 2: return launch_fused_cl<NB, TAILS, 2>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+        default: return launch_fused_cl<NB, TAILS, 3>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+    }
 }
 
 }  // namespace tc

@@ -17,9 +17,12 @@ constexpr int THREADS = 384;        // warpgroup 0: TMA + MMA warps (2 idle); wa
 constexpr int DRAIN_SLABS_LINEAR = 2;   // dense layers: K = 32 (12 MMAs) -- their outputs feed log p directly
 constexpr int DRAIN_SLABS_FUSED = 4;    // fused coupling: K = 64 (24 MMAs) -- its outputs are spline logits
 constexpr int HALF = BN_MAX / 2;     // columns per epilogue warp
-constexpr int A_BYTES = BM * BK * 4;             // 16 KB
-constexpr int B_BYTES = BN_MAX * BK * 4;         // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
+constexpr int A_BYTES = BM * BK * 4;             // 8 KB
+constexpr int B_BYTES = BN_MAX * BK * 4;         // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 KB
+// CTA-pair kernels hold half of every B tile per CTA: 32 KB stages, six of them in the same 192 KB
+constexpr int PAIR_STAGE_BYTES = 2 * A_BYTES + B_BYTES;
+constexpr int PAIR_STAGES = 6;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -70,6 +73,60 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// ---- CTA-pair (cta_group::2) variants.  The two CTAs of a cluster sit on the two SMs of one TPC; ONE tcgen05.mma issued by
+// the leader (cluster rank 0) drives both tensor cores on a 256-row tile: each CTA supplies its own 128 A rows and HALF of
+// the B tile from its own shared memory, which halves the shared-memory operand traffic per SM -- the limiter of the
+// single-CTA form (A + full B read from smem for every MMA: ~97 B/clk of the SM's 128 B/clk while the pipe is busy).
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {          // same smem offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {      // acquires remote (peer CTA) arrivals
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// TMA load into THIS CTA's smem whose bytes are counted on the LEADER CTA's mbarrier (`leader_bar` = mapa_rank(bar, 0))
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {     // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {         // arrives at `bar`'s offset in every CTA of mask
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -132,8 +189,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
            ((uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61);
 }
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int bn, int m = BM) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 
