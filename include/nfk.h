@@ -96,6 +96,13 @@ int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const f
                       const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy, float* y_hi, float* y_lo,
                       int64_t lds, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
                       int32_t out_features, void* stream);
+/* Same layer with the activation operand given as plain fp32 `a` (what the producing kernel wrote): the kernel splits
+ * pre(a) (pre = relu if relu_in) into the (hi, lo) pair on chip, in shared memory, between the TMA load and the MMA, so no
+ * split pair of the activations ever exists in HBM.  Weights still arrive pre-split.  Outputs must not alias `a`. */
+int nfk_linear_tf32x3_a32(const float* a, int64_t lda, int relu_in, const float* w_hi, const float* w_lo, int64_t ldw,
+                          const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy, float* y_hi, float* y_lo,
+                          int64_t lds, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
+                          int32_t out_features, void* stream);
 /* hi[n, j], lo[n, j] = split of pre(x[n*ldx + (cols ? cols[j] : j)]), pre = relu if `relu`.  Produces the operand pairs
  * nfk_linear_tf32x3 consumes (activations entering a layer chain, and weights once per parameter update).  If copy_dst is
  * not NULL the raw values are also copied to copy_dst[n*ldc + col] (the identity half of a coupling output). */
@@ -109,10 +116,9 @@ int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_c
  *   a_hi/a_lo  : split pair of the last hidden activation [n_rows, hidden_features]
  *   wp_hi/wp_lo: split pair of the PACKED final weight [d_t * MP, hidden_features]: row j*MP + k = reference row j*M + k
  *                for k < M, zero rows for M <= k < MP, MP = nfk_rq_coupling_final_padded_params(num_bins, tails)
- *   bias_packed: packed the same way and zero-padded to a whole number of tiles: [ceil(d_t / (2*FPT)) * 2*FPT * MP] with
- *                FPT = 128 / MP (the kernel adds it per tile column)
- * Writes y[n, t_cols[j]] for every transformed feature (the caller copies the identity columns, e.g. with the
- * copy_dst of nfk_split_tf32) and adds the row's log|det| to lad_accum.  nfk_rq_coupling_final_supported says whether an
+ *   bias_packed: packed the same way, [d_t * MP]
+ * Writes y[n, t_cols[j]] for every transformed feature and adds the row's log|det| to lad_accum.  y may be x itself
+ * (in place: the identity columns then need no copy); otherwise the caller fills the identity columns of y.  nfk_rq_coupling_final_supported says whether an
  * instance exists for (num_bins, tails, hidden_features, lda); otherwise use nfk_linear* + nfk_rqs_rows. */
 int nfk_rq_coupling_final_supported(int32_t num_bins, int32_t linear_tails, int32_t hidden_features, int64_t lda);
 int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t linear_tails);

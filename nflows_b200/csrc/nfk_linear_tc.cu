@@ -47,6 +47,7 @@ struct Params {
     int split_relu;          // relu applied before splitting (the next layer consumes relu(y))
     int num_m_tiles, num_n_tiles;
     int n_inner;             // tile schedule, see tile_of()
+    int relu_in;             // A32 kernels: relu applied to A while it is split in shared memory
 };
 
 // Tile schedule of a persistent CTA.  With at least one 128-row block per CTA ("n_inner") a CTA walks all column tiles of
@@ -71,7 +72,11 @@ __device__ __forceinline__ bool tile_of(const int it, const int n_inner, const i
     return t < units * num_n;
 }
 
-template <int CL>
+// A32 = the A operand arrives as plain fp32: the TMA producer lands the raw K-slab in the "hi" half of the stage and the
+// two otherwise idle warps of warpgroup 0 split it IN PLACE (hi = rna_tf32(pre(a)) over the raw bytes, lo = pre(a) - hi
+// into the "lo" half; elementwise, so the TMA swizzle pattern is preserved) before the MMA thread may read the stage.
+// Producers then write ONE fp32 tensor instead of a (hi, lo) pair and the stand-alone split passes disappear.
+template <int CL, bool A32>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -82,14 +87,16 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     const uint32_t bars = smem_base + STAGES * STAGE_BYTES;                // 8-byte mbarriers
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_tfull = bars + 16 * STAGES, bar_tempty = bars + 16 * STAGES + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+    const uint32_t bar_split = bars + 16 * STAGES + 32;                    // A32: stage has been split by warps 2-3
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 24 * STAGES + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_k = (p.K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); mbar_init(bar_split + 8 * s, 2);
+        }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -108,7 +115,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 0) {
         // ================================================= TMA producer
         if (lane == 0) {
-            const uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)p.BN * BK * 4u;
+            const uint32_t tx_bytes = (A32 ? 1u : 2u) * A_BYTES + 2u * (uint32_t)p.BN * BK * 4u;
             int stage = 0; uint32_t phase = 0;
             int tm, tn;
             const int wrows = p.BN / CL;                                   // weight rows this CTA fetches per slab
@@ -121,7 +128,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     mbar_expect_tx(full, tx_bytes);
                     tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
-                    tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
+                    if (!A32) tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
                     if (CL == 1) {
                         tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n0);
                         tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n0);
@@ -156,6 +163,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         int st = stage; uint32_t ph = phase;
                         for (int j = 0; j < pair; ++j) {
                             mbar_wait(bar_full + 8 * st, ph);              // TMA bytes have landed
+                            if (A32) mbar_wait(bar_split + 8 * st, ph);     // ... and A has been split in place
                             if (++st == STAGES) { st = 0; ph ^= 1; }
                         }
                         tc_fence_after();
@@ -188,6 +196,35 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     if (leader) umma_commit(bar_tfull + 8 * acc);                      // partial sum complete -> drain
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
+            }
+        }
+    } else if (A32) {
+        // ================================================= warps 2-3: split the raw A slab of every stage in place
+        const int t = (warp - 2) * 32 + lane;                                 // 64 threads x 8 float4 = one 8 KB slab
+        int stage = 0; uint32_t phase = 0;
+        int tm, tn;
+        for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
+            for (int ks = 0; ks < num_k; ++ks) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                float4* hi = reinterpret_cast<float4*>(smem_gen + stage * STAGE_BYTES);
+                float4* lo = reinterpret_cast<float4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
+#pragma unroll
+                for (int b = 0; b < A_BYTES / 16 / 64; b += 4) {
+                    float4 v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) v[i] = hi[t + 64 * (b + i)];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (p.relu_in) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
+                        const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
+                        hi[t + 64 * (b + i)] = h;
+                        lo[t + 64 * (b + i)] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_split + 8 * stage);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     }
@@ -443,20 +480,24 @@ extern "C" int nfk_linear_tf32x3_supported(int64_t lda, int64_t ldw, int32_t in_
     return (in_features >= 4 && in_features % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0) ? 1 : 0;
 }
 
-extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo,
-                                 int64_t ldw, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
-                                 float* y_hi, float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
-                                 int32_t in_features, int32_t out_features, void* stream) {
+// a_lo == nullptr selects the A32 kernels: `a_hi` is then the plain fp32 activation, split (after an optional relu) on chip
+static int launch_linear(const float* a_hi, const float* a_lo, int relu_in, int64_t lda, const float* w_hi, const float* w_lo,
+                         int64_t ldw, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
+                         float* y_hi, float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
+                         int32_t in_features, int32_t out_features, void* stream) {
+    const bool a32 = a_lo == nullptr;
     NFK_REQUIRE(n_rows >= 0 && in_features >= 1 && out_features >= 1, "bad sizes");
     if (n_rows == 0) return NFK_OK;
-    NFK_REQUIRE(a_hi && a_lo && w_hi && w_lo, "NULL operand pointer");
+    NFK_REQUIRE(a_hi && w_hi && w_lo, "NULL operand pointer");
     NFK_REQUIRE(Y || (y_hi && y_lo), "no output requested");
     NFK_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "y_hi and y_lo must be given together");
     NFK_REQUIRE(nfk_linear_tf32x3_supported(lda, ldw, in_features), "tf32x3 path needs in_features, lda, ldw multiples of 4");
     NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(w_hi) && aligned16(w_lo), "operands must be 16-byte aligned");
     NFK_REQUIRE(n_rows < (1ll << 31), "n_rows too large for one launch");
+    NFK_REQUIRE(!a32 || (Y != a_hi && y_hi != a_hi && y_lo != a_hi), "outputs must not alias the input");
 
     tc::Params p;
+    p.relu_in = relu_in;
     p.bias = bias; p.residual = R; p.y = Y; p.y_hi = y_hi; p.y_lo = y_lo;
     p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
     p.relu_out = relu_out; p.split_relu = split_relu;
@@ -476,15 +517,19 @@ extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t l
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     int rc;
     if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, in_features, lda, tc::BM))) return rc;
-    if ((rc = tc::make_map(&ma_lo, a_lo, n_rows, in_features, lda, tc::BM))) return rc;
+    if ((rc = tc::make_map(&ma_lo, a32 ? a_hi : a_lo, n_rows, in_features, lda, tc::BM))) return rc;
     if ((rc = tc::make_map(&mw_hi, w_hi, out_features, in_features, ldw, bn / CL))) return rc;
     if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn / CL))) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::SMEM_BYTES, cudaGetErrorString(e));
         attr_set = true;
     }
@@ -502,8 +547,30 @@ extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t l
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, p)
-                               : cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    cudaError_t le;
+    if (a32)
+        le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<2, true>, ma_hi, ma_lo, mw_hi, mw_lo, p)
+                       : cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<1, true>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    else
+        le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<2, false>, ma_hi, ma_lo, mw_hi, mw_lo, p)
+                       : cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<1, false>, ma_hi, ma_lo, mw_hi, mw_lo, p);
     if (le != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(linear_tf32x3_kernel, cluster %d): %s", CL, cudaGetErrorString(le));
     return check_launch("linear_tf32x3_kernel");
+}
+
+extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo,
+                                 int64_t ldw, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
+                                 float* y_hi, float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
+                                 int32_t in_features, int32_t out_features, void* stream) {
+    NFK_REQUIRE(a_lo, "NULL operand pointer");
+    return launch_linear(a_hi, a_lo, 0, lda, w_hi, w_lo, ldw, bias, R, ldr, Y, ldy, y_hi, y_lo, lds, relu_out, split_relu, n_rows,
+                         in_features, out_features, stream);
+}
+
+extern "C" int nfk_linear_tf32x3_a32(const float* a, int64_t lda, int relu_in, const float* w_hi, const float* w_lo, int64_t ldw,
+                                     const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy, float* y_hi,
+                                     float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
+                                     int32_t in_features, int32_t out_features, void* stream) {
+    return launch_linear(a, nullptr, relu_in, lda, w_hi, w_lo, ldw, bias, R, ldr, Y, ldy, y_hi, y_lo, lds, relu_out, split_relu,
+                         n_rows, in_features, out_features, stream);
 }

@@ -362,7 +362,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 for (int f = 0; f < FPT; ++f) {
                     const bool ok = row_ok && (j0 + f < p.d_t);
                     col[f] = ok ? __ldg(p.t_cols + j0 + f) : 0;
-                    xin[f] = ok ? __ldg(p.x + row * p.ldx + col[f]) : 0.0f;
+                    xin[f] = ok ? p.x[row * p.ldx + col[f]] : 0.0f;       // plain load: y may alias x (each element is read, then written, by this thread only)
                 }
                 // running sums start from the packed bias of this thread's columns; all loads are issued back-to-back here -- a
                 // load/add pair per column inside the first drain serialised 120 L1 latencies per tile (ncu: 37 % of the
@@ -528,7 +528,6 @@ extern "C" int nfk_rq_coupling_final_tf32x3(const NfkSplineDesc* desc, int inver
     NFK_REQUIRE(nfk_rq_coupling_final_supported(desc->num_bins, desc->linear_tails, hidden_features, lda) && ldw % 4 == 0,
                 "fused coupling kernel does not take num_bins=%d hidden=%d", desc->num_bins, hidden_features);
     NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(wp_hi) && aligned16(wp_lo), "operands must be 16-byte aligned");
-    NFK_REQUIRE(x != y, "y must not alias x");
     NFK_REQUIRE(n_rows < (1ll << 31), "n_rows too large for one launch");
     p.bias = bias_packed; p.x = x; p.y = y; p.t_cols = t_cols; p.lad_accum = lad_accum; p.flags = flags;
     p.ldx = ldx; p.ldy = ldy; p.n_rows = n_rows; p.K = hidden_features; p.d_t = d_t; p.inverse = inverse;

@@ -46,49 +46,64 @@ def chain_uses_tc(chain, first_in_features):
 
 
 class ChainState:
-    """Activation between two layers: fp32 tensor (`raw`) and/or the split pair the next tensor-core layer consumes."""
+    """Activation between two layers: fp32 tensor (`raw`) and/or the split pair a tensor-core layer consumes."""
 
     def __init__(self, raw=None, pair=None):
         self.raw, self.pair = raw, pair
 
 
-def run_trunk(chain, x, id_cols, use_tc, copy_identity_to=None):
-    """All layers of `chain` but the last, on the identity columns of x.  Returns the ChainState feeding the last layer.
-    copy_identity_to: coupling output whose identity columns are filled on the way (tensor-core path only).
-    The tensor-core path walks row sub-blocks so that every intermediate of a sub-block stays L2-resident."""
+def run_trunk(chain, x, id_cols, use_tc, want_pair=False, x_id=None):
+    """All layers of `chain` but the last, on the identity columns of x.  Returns the ChainState feeding the last layer:
+    the split pair of its (pre-activated) input when want_pair, else the fp32 tensor.
+    x_id: the identity columns as a (possibly strided) view when they are contiguous in x -- no gather pass then.
+    The tensor-core path walks row sub-blocks so that the intermediates of a sub-block are reused out of L2."""
     from . import config
     n = x.shape[0]
     step = max(128, int(config.trunk_block_rows))
     if use_tc and n > step and len(chain) > 1:
         width = chain[-2][0].shape[0]
-        hi = torch.empty(n, width, dtype=torch.float32, device=x.device)
-        lo = torch.empty_like(hi)
+        if want_pair:
+            dst = (torch.empty(n, width, dtype=torch.float32, device=x.device),
+                   torch.empty(n, width, dtype=torch.float32, device=x.device))
+        else:
+            dst = torch.empty(n, width, dtype=torch.float32, device=x.device)
         for r0 in range(0, n, step):
             r1 = min(n, r0 + step)
-            sub = _run_trunk_block(chain, x[r0:r1], id_cols, True,
-                                   None if copy_identity_to is None else copy_identity_to[r0:r1], (hi[r0:r1], lo[r0:r1]))
-        return ChainState(raw=None, pair=(hi, lo))
-    return _run_trunk_block(chain, x, id_cols, use_tc, copy_identity_to, None)
+            _run_trunk_block(chain, x[r0:r1], id_cols, True,
+                             (dst[0][r0:r1], dst[1][r0:r1]) if want_pair else dst[r0:r1], want_pair,
+                             None if x_id is None else x_id[r0:r1])
+        return ChainState(pair=dst) if want_pair else ChainState(raw=dst)
+    return _run_trunk_block(chain, x, id_cols, use_tc, None, want_pair, x_id)
 
 
-def _run_trunk_block(chain, x, id_cols, use_tc, copy_identity_to, last_pair_out):
+def _run_trunk_block(chain, x, id_cols, use_tc, last_out, want_pair, x_id=None):
     body = chain[:-1]
     last_relu_in = chain[-1][2]
     if use_tc:
-        state = ChainState(pair=K.split_tf32(x, id_cols, relu=body[0][2] if body else last_relu_in,
-                                             copy_to=copy_identity_to))
-        skip_src = None
+        # every layer reads the fp32 activation its producer wrote and splits it on chip (nfk_linear_tf32x3_a32); only the
+        # input of the LAST layer is materialised as a split pair when the fused coupling kernel (which re-reads it once per
+        # column tile) consumes it
+        if x_id is None:
+            x_id = x if id_cols is None else K.gather_cols(x, id_cols)
+        if not body:
+            return ChainState(pair=K.split_tf32(x_id, relu=last_relu_in)) if want_pair else ChainState(raw=x_id)
+        hidden, skip_src = x_id, None
+        state = None
         for i, (weight, bias, relu_in, relu_out, residual) in enumerate(body):
-            nxt_relu_in = chain[i + 1][2]
-            need_raw = i + 2 < len(chain) and chain[i + 2][4] == "skip"
+            last = i == len(body) - 1
             res = skip_src if residual == "skip" else None
-            y, pair = K.linear_tf32x3(state.pair, split_weight(weight), bias.detach() if bias is not None else None,
-                                      residual=res, relu_out=relu_out, want_y=need_raw, want_split=True,
-                                      split_relu=nxt_relu_in,
-                                      pair_out=last_pair_out if i == len(body) - 1 else None)
-            if need_raw:
-                skip_src = y
-            state = ChainState(raw=y, pair=pair)
+            b = bias.detach() if bias is not None else None
+            if last and want_pair:
+                _, pair = K.linear_tf32x3(hidden, split_weight(weight), b, residual=res, relu_in=relu_in, relu_out=relu_out,
+                                          want_y=False, want_split=True, split_relu=last_relu_in, pair_out=last_out)
+                state = ChainState(pair=pair)
+            else:
+                y, _ = K.linear_tf32x3(hidden, split_weight(weight), b, residual=res, relu_in=relu_in, relu_out=relu_out,
+                                       want_y=True, y_out=last_out if last else None)
+                state = ChainState(raw=y)
+                if i + 2 < len(chain) and chain[i + 2][4] == "skip":
+                    skip_src = y                       # input of the residual block that starts with the next layer
+                hidden = y
         return state
     hidden = x if id_cols is None else K.gather_cols(x, id_cols)
     branch = None
@@ -108,14 +123,12 @@ def run_last(chain, state, r0, r1, use_tc):
     weight, bias, relu_in, relu_out, _ = chain[-1]
     b = bias.detach() if bias is not None else None
     if use_tc:
-        pair = (state.pair[0][r0:r1], state.pair[1][r0:r1])
-        return K.linear_tf32x3(pair, split_weight(weight), b, relu_out=relu_out, want_y=True)[0]
+        return K.linear_tf32x3(state.raw[r0:r1], split_weight(weight), b, relu_in=relu_in, relu_out=relu_out, want_y=True)[0]
     return K.linear(state.raw[r0:r1], weight.detach(), b, relu_in=relu_in, relu_out=relu_out)
 
 
 def affine_map(x, weight, bias):
-    """y = x @ weight.T + bias for a folded ActNorm/Permutation/LU run, in row sub-blocks small enough that the split pair
-    written by `split_tf32` is still in L2 when the GEMM reads it."""
+    """y = x @ weight.T + bias for a folded ActNorm/Permutation/LU run: one tensor-core GEMM reading x as it is."""
     from . import config
     n, k = x.shape
     if backend() == "tc" and K.tf32x3_supported(x.stride(0), weight.stride(0), k):
@@ -124,7 +137,7 @@ def affine_map(x, weight, bias):
         step = max(128, int(config.affine_block_rows))
         for r0 in range(0, n, step):
             r1 = min(n, r0 + step)
-            K.linear_tf32x3(K.split_tf32(x[r0:r1]), w_pair, bias, want_y=True, y_out=y[r0:r1])
+            K.linear_tf32x3(x[r0:r1], w_pair, bias, want_y=True, y_out=y[r0:r1])
         return y
     return K.linear(x, weight, bias)
 

@@ -177,12 +177,16 @@ def tf32x3_supported(lda, ldw, in_features):
     return bool(N.load().nfk_linear_tf32x3_supported(int(lda), int(ldw), int(in_features)))
 
 
-def linear_tf32x3(a_pair, w_pair, bias=None, residual=None, relu_out=False, want_y=True, want_split=False,
+def linear_tf32x3(a, w_pair, bias=None, residual=None, relu_in=False, relu_out=False, want_y=True, want_split=False,
                   split_relu=False, y_out=None, pair_out=None):
-    """tcgen05 dense layer on split operands.  Returns (y or None, (y_hi, y_lo) or None); y_out / pair_out are
-    caller-provided destinations (row slices of larger buffers)."""
-    a_hi, a_lo = a_pair
+    """tcgen05 dense layer.  `a` is either the (hi, lo) split pair of the activations or the plain fp32 activation tensor,
+    which the kernel splits on chip (after relu when relu_in).  Returns (y or None, (y_hi, y_lo) or None); y_out /
+    pair_out are caller-provided destinations (row slices of larger buffers)."""
     w_hi, w_lo = w_pair
+    raw = not isinstance(a, tuple)
+    a_hi = _rows2d(a, "a") if raw else a[0]
+    if not raw and relu_in:
+        raise ValueError("relu_in needs the fp32 activation, not a split pair")
     n, k = a_hi.shape
     o = w_hi.shape[0]
     dev = a_hi.device
@@ -194,19 +198,15 @@ def linear_tf32x3(a_pair, w_pair, bias=None, residual=None, relu_out=False, want
         pair = None
     if bias is not None and not bias.is_contiguous():
         bias = bias.contiguous()
-    if TIMELINE is not None:
-        with timed("linear_%dx%d" % (k, o), n):
-            N.check(N.lib().nfk_linear_tf32x3(
-                a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N.ptr(bias),
-                N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y), y.stride(0) if y is not None else 0,
-                N.ptr(pair[0]) if pair else 0, N.ptr(pair[1]) if pair else 0, pair[0].stride(0) if pair else 0, int(relu_out),
-                int(split_relu), n, k, o, N.stream()))
-        return y, pair
-    N.check(N.lib().nfk_linear_tf32x3(
-        a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N.ptr(bias),
-        N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y), y.stride(0) if y is not None else 0,
-        N.ptr(pair[0]) if pair else 0, N.ptr(pair[1]) if pair else 0, pair[0].stride(0) if pair else 0, int(relu_out),
-        int(split_relu), n, k, o, N.stream()))
+    tail = (w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N.ptr(bias),
+            N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y), y.stride(0) if y is not None else 0,
+            N.ptr(pair[0]) if pair else 0, N.ptr(pair[1]) if pair else 0, pair[0].stride(0) if pair else 0, int(relu_out),
+            int(split_relu), n, k, o, N.stream())
+    with timed("linear_%dx%d" % (k, o), n):
+        if raw:
+            N.check(N.lib().nfk_linear_tf32x3_a32(a_hi.data_ptr(), a_hi.stride(0), int(relu_in), *tail))
+        else:
+            N.check(N.lib().nfk_linear_tf32x3(a_hi.data_ptr(), a[1].data_ptr(), a_hi.stride(0), *tail))
     return y, pair
 
 

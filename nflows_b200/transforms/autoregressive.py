@@ -157,12 +157,13 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
         all_cols, no_cols = self._cols(spline_input.device)
         use_tc = D.chain_uses_tc(chain, self.features)
         outputs = torch.empty_like(spline_input, memory_format=torch.contiguous_format)
-        state = D.run_trunk(chain, conditioner_input, None, use_tc)
         desc = self._spline_desc()
         weight, bias = chain[-1][0], chain[-1][1]
         hidden = weight.shape[1]
-        if (use_tc and config.fuse_coupling and bias is not None
-                and K.rq_coupling_final_supported(self.num_bins, self.tails, hidden, hidden)):
+        fused = (use_tc and config.fuse_coupling and bias is not None
+                 and K.rq_coupling_final_supported(self.num_bins, self.tails, hidden, hidden))
+        state = D.run_trunk(chain, conditioner_input, None, use_tc, want_pair=fused)
+        if fused:
             m = self._output_dim_multiplier()
             mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
             wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.features, m, mp)

@@ -99,11 +99,25 @@ class CompositeTransform(Transform):
         return K.native_ok(inputs) and inputs.dim() == 2 and params_frozen(self)
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
+        """Walks the flattened leaves.  Between leaves the tensor may live in a permuted COLUMN LAYOUT (fused_affine.Layout):
+        a coupling that runs on the fused tensor-core path asks for its identity features first / transformed features
+        last; the folded affine run in front of it emits that order for free (a row permutation of its weight matrix) and
+        the run behind it absorbs it (a column permutation), so the flow state is never gathered, scattered or copied
+        between layers.  Leaves that know nothing about layouts always see the logical column order."""
         from .fused_affine import AffineRun, is_affine_leaf
 
         leaves = _flatten(self, inverse, [])
         x = inputs
+        layout = None            # None = logical column order
+        owned = False            # x is a temporary of this chain (may be overwritten in place)
         i = 0
+
+        def wanted(k):
+            if k >= len(leaves):
+                return None
+            fn = getattr(leaves[k][0], "_native_layout", None)
+            return fn(x, context) if fn is not None else None
+
         while i < len(leaves):
             leaf, inv = leaves[i]
             # fold a run of per-feature affine / permutation / LU transforms into ONE dense layer
@@ -114,18 +128,34 @@ class CompositeTransform(Transform):
                 j += 1
             if has_lu and j - i >= 1:
                 run = AffineRun.cached(self._affine_cache, leaves[i:j], x.device)
-                x = run.apply(x, lad)
+                out_layout = wanted(j)
+                x = run.apply(x, lad, layout, out_layout)
+                layout, owned = out_layout, True
                 i = j
                 continue
-            if leaf._native_ready(x, context):
+            want = wanted(i) if leaf._native_ready(x, context) else None
+            if layout is not None and layout is not want:
+                x = K.gather_cols(x, layout.cols(x.device, inverse=True))       # back to the logical order
+                layout, owned = None, True
+            if want is not None and layout is None:
+                x = K.gather_cols(x, want.cols(x.device))
+                layout, owned = want, True
+            if layout is not None:
+                x = leaf._native_apply(x, lad, flags, inv, context, layout=layout, owned=owned)
+                owned = True
+            elif leaf._native_ready(x, context):
                 x = leaf._native_apply(x, lad, flags, inv, context)
+                owned = True
             else:
                 x, l = leaf.inverse(x, context) if inv else leaf(x, context)
                 lad += l
                 if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
                     raise RuntimeError("{} changed the tensor layout inside a native chain".format(type(leaf).__name__))
                 x = x.contiguous()
+                owned = True
             i += 1
+        if layout is not None:
+            x = K.gather_cols(x, layout.cols(x.device, inverse=True))
         return x
 
 

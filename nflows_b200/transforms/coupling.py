@@ -46,6 +46,9 @@ class CouplingTransform(Transform):
         else:
             self.unconditional_transform = unconditional_transform(features=self.num_identity_features)
         self._col_cache = None
+        self._layout_cache = None
+        self._packed_cols = None
+        self._all_cols = None
 
     @property
     def num_identity_features(self):
@@ -104,8 +107,47 @@ class CouplingTransform(Transform):
         rows = (config.param_chunk_mib << 20) // (4 * max(1, n_params))
         return int(max(256, min(1 << 16, rows // 128 * 128)))
 
-    def _native_apply(self, inputs, lad, flags, inverse, context=None):
+    def _native_layout(self, inputs, context):
+        """Column order this coupling wants its input in -- identity features first, transformed features last -- when it
+        runs on the fused tensor-core path (CompositeTransform._native_apply arranges it), else None."""
+        if self.unconditional_transform is not None or not self._native_ready(inputs, context):
+            return None
+        net = self.transform_net
+        chain = net.dense_chain(context) if hasattr(net, "dense_chain") else None
+        if chain is None or not D.chain_uses_tc(chain, self.num_identity_features) or not self._fused_final_ready(chain):
+            return None
+        if (self.num_identity_features % 4) or (self.features % 4):
+            return None                                   # the strided identity view must be TMA-addressable
+        idf, tf = self.identity_features, self.transform_features
+        key = (idf.data_ptr(), idf._version, tf.data_ptr(), tf._version)
+        if self._layout_cache is None or self._layout_cache[0] != key:
+            from .fused_affine import Layout
+            self._layout_cache = (key, Layout(torch.cat([idf, tf]).cpu().numpy()))
+        return self._layout_cache[1]
+
+    def _native_packed(self, x, lad, flags, inverse, context, owned):
+        """Fused path on a tensor already in the [identity | transformed] column order: the conditioner trunk reads the
+        identity block as a strided view, the fused kernel overwrites the transformed block in place; nothing is copied."""
+        if not owned:
+            x = x.clone()
+        d_id = self.num_identity_features
+        if self._packed_cols is None or self._packed_cols.device != x.device:
+            self._packed_cols = torch.arange(d_id, self.features, dtype=torch.int32, device=x.device)
+        chain = self.transform_net.dense_chain(context)
+        n = x.shape[0]
+        block = 1 << 18
+        for r0 in range(0, n, block):
+            r1 = min(n, r0 + block)
+            xs = x[r0:r1]
+            state = D.run_trunk(chain, xs, None, True, want_pair=True, x_id=xs[:, :d_id])
+            with K.timed("rq_coupling_final", r1 - r0):
+                self._fused_final(chain, state, xs, self._packed_cols, xs, lad[r0:r1], flags, inverse)
+        return x
+
+    def _native_apply(self, inputs, lad, flags, inverse, context=None, layout=None, owned=False):
         self._check_inputs(inputs)
+        if layout is not None:
+            return self._native_packed(inputs, lad, flags, inverse, context, owned)
         if self.unconditional_transform is None:
             return self._native_coupling(inputs, lad, flags, inverse, context)
         # identity half additionally goes through its own elementwise transform (coupling.py:90-94 forward: after the
@@ -134,13 +176,24 @@ class CouplingTransform(Transform):
         use_tc = chain is not None and D.chain_uses_tc(chain, self.num_identity_features)
         final_rows = self._conditioner_rows(n_params)
         if use_tc and self._fused_final_ready(chain):
-            # the north-star shape: trunk GEMMs, then ONE kernel = final layer + spline + scatter + log|det|
+            # stand-alone call (no composite arranging the column order): gather into [identity | transformed], run the
+            # packed path in place, scatter back
+            layout = self._native_layout(inputs, context)
+            if layout is not None:
+                packed = self._native_packed(K.gather_cols(inputs, layout.cols(inputs.device)), lad, flags, inverse, context,
+                                             True)
+                return K.gather_cols(packed, layout.cols(inputs.device, inverse=True), out=outputs)
+            # feature count not a multiple of 4 (no TMA-addressable identity view): gathered trunk input, full copy of the
+            # input as the output, transformed columns overwritten in place
+            if self._all_cols is None or self._all_cols.device != inputs.device:
+                self._all_cols = torch.arange(self.features, dtype=torch.int32, device=inputs.device)
+            K.gather_cols(inputs, self._all_cols, out=outputs)
             block = 1 << 18
             for r0 in range(0, n, block):
                 r1 = min(n, r0 + block)
-                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, copy_identity_to=outputs[r0:r1])
+                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, want_pair=True)
                 with K.timed("rq_coupling_final", r1 - r0):
-                    self._fused_final(chain, state, inputs[r0:r1], t_cols, outputs[r0:r1], lad[r0:r1], flags, inverse)
+                    self._fused_final(chain, state, outputs[r0:r1], t_cols, outputs[r0:r1], lad[r0:r1], flags, inverse)
             return outputs
         for r0 in range(0, n, trunk_rows):
             r1 = min(n, r0 + trunk_rows)

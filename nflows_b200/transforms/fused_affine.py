@@ -13,6 +13,24 @@ from .. import dense as D
 from .. import kernels as K
 
 
+class Layout:
+    """Physical column order of the tensor between two leaves: physical column j holds logical feature perm[j]."""
+
+    def __init__(self, perm):
+        self.perm = np.asarray(perm, dtype=np.int64)
+        self.inv = np.argsort(self.perm, kind="stable")
+        self._dev = {}
+
+    def cols(self, device, inverse=False):
+        """int32 gather index on `device`: logical -> physical (x_phys = x[:, cols]) or, inverse, physical -> logical."""
+        key = (str(device), inverse)
+        t = self._dev.get(key)
+        if t is None:
+            t = torch.from_numpy((self.inv if inverse else self.perm).astype(np.int32)).to(device)
+            self._dev[key] = t
+        return t
+
+
 def is_affine_leaf(leaf, x):
     from .lu import LULinear
     from .normalization import ActNorm
@@ -81,9 +99,26 @@ class AffineRun:
                     perm = np.argsort(perm, kind="stable")
                 A = A[perm, :]
                 c = c[perm]
-        self.weight = torch.from_numpy(np.ascontiguousarray(A)).float().to(device)
-        self.bias = torch.from_numpy(np.ascontiguousarray(c)).float().to(device)
+        self._A, self._c, self._device = A, c, device
+        self._operands = {}
+        self.weight, self.bias = self.operands(None, None)
         self.lad_const = float(lad)
+
+    def operands(self, in_layout, out_layout):
+        """(weight, bias) acting on a tensor stored in `in_layout` and producing `out_layout`: rows of A follow the output
+        order, columns the input order (entries are only moved, so the rounding to fp32 is the same as unpermuted)."""
+        key = (id(in_layout), id(out_layout))
+        hit = self._operands.get(key)
+        if hit is None:
+            A, c = self._A, self._c
+            if out_layout is not None:
+                A, c = A[out_layout.perm, :], c[out_layout.perm]
+            if in_layout is not None:
+                A = A[:, in_layout.perm]
+            hit = (torch.from_numpy(np.ascontiguousarray(A)).float().to(self._device),
+                   torch.from_numpy(np.ascontiguousarray(c)).float().to(self._device), in_layout, out_layout)
+            self._operands[key] = hit
+        return hit[0], hit[1]
 
     @classmethod
     def cached(cls, cache, leaves, device):
@@ -95,8 +130,9 @@ class AffineRun:
             cache[key] = hit
         return hit[1]
 
-    def apply(self, x, lad):
-        y = D.affine_map(x, self.weight, self.bias)
+    def apply(self, x, lad, in_layout=None, out_layout=None):
+        weight, bias = self.operands(in_layout, out_layout)
+        y = D.affine_map(x, weight, bias)
         if self.lad_const != 0.0:
             K.add_const_(lad, self.lad_const)
         return y

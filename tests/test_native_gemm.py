@@ -57,6 +57,27 @@ def test_linear_tf32x3(cuda_device, n, k, o):
 
 
 @torch.no_grad()
+@pytest.mark.parametrize("n,k,o", SHAPES)
+def test_linear_tf32x3_fp32_activation_split_on_chip(cuda_device, n, k, o):
+    """nfk_linear_tf32x3_a32: A given as plain fp32 (here a strided column block of a wider tensor, as the coupling trunk
+    reads the identity features), relu + split done in shared memory; must match the pre-split path bit for bit."""
+    g = torch.Generator(device=cuda_device).manual_seed(7 * n + k + o)
+    wide = torch.randn(n, 2 * k, device=cuda_device, generator=g)
+    x = wide[:, :k]
+    w = torch.randn(o, k, device=cuda_device, generator=g) / k ** 0.5
+    b = torch.randn(o, device=cuda_device, generator=g)
+    r = torch.randn(n, o, device=cuda_device, generator=g)
+    wp = K.split_tf32(w)
+    for relu_in, relu_out, res in ((False, False, None), (True, True, None), (True, False, r)):
+        y, pair = K.linear_tf32x3(x, wp, b, residual=res, relu_in=relu_in, relu_out=relu_out, want_y=True, want_split=True)
+        assert rel_err(y, reference(x, w, b, res, relu_in, relu_out)) <= 8e-6, (n, k, o, relu_in, relu_out)
+        assert torch.equal(pair[0] + pair[1], y)
+        y2, _ = K.linear_tf32x3(K.split_tf32(x.contiguous(), relu=relu_in), wp, b, residual=res, relu_out=relu_out)
+        assert torch.equal(y, y2)
+        assert torch.equal(wide[:, :k], x)                         # the in-place split happens in shared memory only
+
+
+@torch.no_grad()
 def test_linear_tf32x3_unsupported_shapes_are_rejected(cuda_device):
     assert not K.tf32x3_supported(3, 3, 3)
     x = torch.randn(10, 6, device=cuda_device)
