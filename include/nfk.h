@@ -126,6 +126,13 @@ int nfk_rq_coupling_final_tf32x3(const NfkSplineDesc* desc, int inverse, const f
                                  const float* wp_hi, const float* wp_lo, int64_t ldw, const float* bias_packed,
                                  int32_t hidden_features, const float* x, int64_t ldx, const int32_t* t_cols, int32_t d_t,
                                  float* y, int64_t ldy, float* lad_accum, int64_t n_rows, int32_t* flags, void* stream);
+/* Same kernel with the hidden activation given as plain fp32 `a` (split on chip after relu when relu_in), as written by
+ * nfk_linear_tf32x3_a32 with Y != NULL: no (hi, lo) pair of the activations in HBM, half the activation operand traffic. */
+int nfk_rq_coupling_final_tf32x3_a32(const NfkSplineDesc* desc, int inverse, const float* a, int64_t lda, int relu_in,
+                                     const float* wp_hi, const float* wp_lo, int64_t ldw, const float* bias_packed,
+                                     int32_t hidden_features, const float* x, int64_t ldx, const int32_t* t_cols,
+                                     int32_t d_t, float* y, int64_t ldy, float* lad_accum, int64_t n_rows,
+                                     int32_t* flags, void* stream);
 
 /* ---- row-wise elementwise transforms -------------------------------------------------------------------- */
 /* out[n, j] = x[n*ldx + cols[j]] (identity_split gather, coupling.py:82; Permutation._permute,

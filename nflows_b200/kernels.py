@@ -218,11 +218,20 @@ def rq_coupling_final_padded_params(num_bins, tails):
     return int(N.load().nfk_rq_coupling_final_padded_params(int(num_bins), 1 if tails == "linear" else 0))
 
 
-def rq_coupling_final(desc, inverse, a_pair, wp_pair, bias_packed, x, t_cols, y, lad_accum, flags):
-    """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel)."""
-    a_hi, a_lo = a_pair
-    N.check(N.lib().nfk_rq_coupling_final_tf32x3(
-        ctypes.byref(desc), int(inverse), a_hi.data_ptr(), a_lo.data_ptr(), a_hi.stride(0), wp_pair[0].data_ptr(),
-        wp_pair[1].data_ptr(), wp_pair[0].stride(0), bias_packed.data_ptr(), a_hi.shape[1], x.data_ptr(), x.stride(0),
-        t_cols.data_ptr(), t_cols.numel(), y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
+def rq_coupling_final(desc, inverse, a, wp_pair, bias_packed, x, t_cols, y, lad_accum, flags, relu_in=False):
+    """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel).  `a`: the (hi, lo) pair of the
+    hidden activation, or the fp32 activation itself (split on chip, after relu when relu_in).  y may be x."""
+    tail = (wp_pair[0].data_ptr(), wp_pair[1].data_ptr(), wp_pair[0].stride(0), bias_packed.data_ptr())
+    rest = (x.data_ptr(), x.stride(0), t_cols.data_ptr(), t_cols.numel(), y.data_ptr(), y.stride(0), N.ptr(lad_accum),
+            x.shape[0], N.ptr(flags), N.stream())
+    if isinstance(a, tuple):
+        if relu_in:
+            raise ValueError("relu_in needs the fp32 activation, not a split pair")
+        a_hi, a_lo = a
+        N.check(N.lib().nfk_rq_coupling_final_tf32x3(ctypes.byref(desc), int(inverse), a_hi.data_ptr(), a_lo.data_ptr(),
+                                                     a_hi.stride(0), *tail, a_hi.shape[1], *rest))
+    else:
+        _rows2d(a, "a")
+        N.check(N.lib().nfk_rq_coupling_final_tf32x3_a32(ctypes.byref(desc), int(inverse), a.data_ptr(), a.stride(0),
+                                                         int(relu_in), *tail, a.shape[1], *rest))
     return y

@@ -139,7 +139,7 @@ class CouplingTransform(Transform):
         for r0 in range(0, n, block):
             r1 = min(n, r0 + block)
             xs = x[r0:r1]
-            state = D.run_trunk(chain, xs, None, True, want_pair=True, x_id=xs[:, :d_id])
+            state = D.run_trunk(chain, xs, None, True, want_pair=config.fused_pair_input, x_id=xs[:, :d_id])
             with K.timed("rq_coupling_final", r1 - r0):
                 self._fused_final(chain, state, xs, self._packed_cols, xs, lad[r0:r1], flags, inverse)
         return x
@@ -191,7 +191,7 @@ class CouplingTransform(Transform):
             block = 1 << 18
             for r0 in range(0, n, block):
                 r1 = min(n, r0 + block)
-                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, want_pair=True)
+                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, want_pair=config.fused_pair_input)
                 with K.timed("rq_coupling_final", r1 - r0):
                     self._fused_final(chain, state, outputs[r0:r1], t_cols, outputs[r0:r1], lad[r0:r1], flags, inverse)
             return outputs
@@ -401,4 +401,5 @@ class PiecewiseRationalQuadraticCouplingTransform(PiecewiseCouplingTransform):
         m = self._transform_dim_multiplier()
         mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
         wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.num_transform_features, m, mp)
-        K.rq_coupling_final(self._spline_desc(), inverse, state.pair, wp_pair, bias_packed, x, t_cols, out, lad, flags)
+        K.rq_coupling_final(self._spline_desc(), inverse, state.pair if state.pair is not None else state.raw, wp_pair,
+                            bias_packed, x, t_cols, out, lad, flags, relu_in=chain[-1][2] and state.pair is None)

@@ -388,6 +388,14 @@ def test_fused_coupling_kernel_matches_unfused_and_oracle(cuda_device, bins, tai
         before = _native.launch_count()
         y1, l1 = run()
         fused_launches = _native.launch_count() - before
+        # same kernel fed with the pre-split (hi, lo) activation pair instead of splitting the fp32 activation on chip:
+        # identical arithmetic, so bit-identical results
+        config.fused_pair_input = True
+        try:
+            y1p, l1p = run()
+        finally:
+            config.fused_pair_input = False
+        assert torch.equal(y1, y1p) and torch.equal(l1, l1p)
         config.fuse_coupling = False
         monkeypatch.setenv("NFLOWS_B200_GEMM", "simt")
         try:
