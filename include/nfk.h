@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NFK_ABI_VERSION 1
+#define NFK_ABI_VERSION 2
 
 #define NFK_OK 0
 #define NFK_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -35,6 +35,7 @@ extern "C" {
 
 #define NFK_FLAG_OUTSIDE_DOMAIN 1  /* constrained spline input outside [left,right] */
 #define NFK_FLAG_NEG_DISCRIMINANT 2 /* inverse spline: b^2-4ac < 0 */
+#define NFK_FLAG_F16_RANGE 4        /* a value left the fp16 range while a split pair was formed (see nfk_linear_f16x3) */
 
 #define NFK_MAX_BINS 64
 
@@ -86,53 +87,45 @@ int nfk_linear(const float* X, int64_t ldx, const float* W, int64_t ldw, const f
                int64_t ldr, float* Y, int64_t ldy, int64_t n_rows, int32_t in_features, int32_t out_features,
                int relu_in, int relu_out, void* stream);
 
-/* Tensor-core version of nfk_linear (tcgen05.mma kind::tf32, TMA-fed, accumulators in TMEM) with fp32-equivalent
- * operand precision: every operand is a split pair v = v_hi + v_lo with v_hi = round-to-nearest TF32 of v (fp32
- * container) and v_lo = v - v_hi, and each K-step accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.  The epilogue can
- * emit the fp32 result Y and/or the split pair of Y (of relu(Y) when split_relu) that the next layer consumes.
- * Requires in_features, lda, ldw multiples of 4 and 16-byte aligned operands (nfk_linear_tf32x3_supported). */
-int nfk_linear_tf32x3_supported(int64_t lda, int64_t ldw, int32_t in_features);
-int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo, int64_t ldw,
-                      const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy, float* y_hi, float* y_lo,
-                      int64_t lds, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
-                      int32_t out_features, void* stream);
-/* Same layer with the activation operand given as plain fp32 `a` (what the producing kernel wrote): the kernel splits
- * pre(a) (pre = relu if relu_in) into the (hi, lo) pair on chip, in shared memory, between the TMA load and the MMA, so no
- * split pair of the activations ever exists in HBM.  Weights still arrive pre-split.  Outputs must not alias `a`. */
-int nfk_linear_tf32x3_a32(const float* a, int64_t lda, int relu_in, const float* w_hi, const float* w_lo, int64_t ldw,
-                          const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy, float* y_hi, float* y_lo,
-                          int64_t lds, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
-                          int32_t out_features, void* stream);
-/* hi[n, j], lo[n, j] = split of pre(x[n*ldx + (cols ? cols[j] : j)]), pre = relu if `relu`.  Produces the operand pairs
- * nfk_linear_tf32x3 consumes (activations entering a layer chain, and weights once per parameter update).  If copy_dst is
- * not NULL the raw values are also copied to copy_dst[n*ldc + col] (the identity half of a coupling output). */
-int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_cols, int relu, float* hi, float* lo,
-                   int64_t ldo, float* copy_dst, int64_t ldc, int64_t n_rows, void* stream);
+/* Tensor-core version of nfk_linear (tcgen05.mma kind::f16, TMA-fed, accumulators in TMEM) with fp32-equivalent
+ * operand precision.  Every operand is a SPLIT PAIR of fp16 tensors with a per-tensor power-of-two scale:
+ *     v * 2^exp = v_hi + v_lo,  v_hi = nearest fp16 of v * 2^exp,  v_lo = nearest fp16 of the exact remainder
+ * (22 mantissa bits; 4 bytes per element for the pair), and each K-step accumulates a_lo*w_hi + a_hi*w_lo + a_hi*w_hi in
+ * fp32; the epilogue multiplies by 2^-(a_exp + w_exp).  Pick exp so that max |v| * 2^exp stays below 65000 and typical
+ * values sit well above 2^-3 (weights: max |w| -> 2^14; activations: a fixed exponent such as 6).
+ * The epilogue can emit the fp32 result Y and/or, for the first split_cols columns (0 = all), the split pair of Y (of
+ * relu(Y) when split_relu) with exponent y_exp that the next layer consumes.  A pair element that leaves the fp16 range
+ * raises NFK_FLAG_F16_RANGE in `flags`.  hi/lo pointers are fp16 device arrays, ld* in ELEMENTS; TMA needs in_features, lda,
+ * ldw multiples of 8 and 16-byte aligned bases (nfk_linear_f16x3_supported). */
+int nfk_linear_f16x3_supported(int64_t lda, int64_t ldw, int32_t in_features);
+int nfk_linear_f16x3(const void* a_hi, const void* a_lo, int64_t lda, int32_t a_exp, const void* w_hi, const void* w_lo,
+                     int64_t ldw, int32_t w_exp, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
+                     void* y_hi, void* y_lo, int64_t lds, int32_t y_exp, int32_t split_cols, int relu_out, int split_relu,
+                     int64_t n_rows, int32_t in_features, int32_t out_features, int32_t* flags, void* stream);
+/* hi[n, j], lo[n, j] = fp16 split pair of pre(x[n*ldx + j]) * 2^scale_exp, pre = relu if `relu`: weights (once per parameter
+ * update), tensors entering a tensor-core chain from outside, the transformed half of a coupling output. */
+int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int relu, int32_t scale_exp, void* hi, void* lo, int64_t ldo,
+                  int64_t n_rows, int32_t* flags, void* stream);
 
 /* ---- fused RQ-coupling step ------------------------------------------------------------------------------------ */
 /* Final conditioner layer + spline + scatter + log|det| in ONE tcgen05 kernel: replaces the last F.linear of the
  * conditioner (nn/nets/resnet.py:99), PiecewiseCouplingTransform._coupling_transform / _piecewise_cdf (coupling.py:279-293,
  * 549-582), the spline (splines/rational_quadratic.py:13-181) and the transform-half scatter (coupling.py:98).
- *   a_hi/a_lo  : split pair of the last hidden activation [n_rows, hidden_features]
- *   wp_hi/wp_lo: split pair of the PACKED final weight [d_t * MP, hidden_features]: row j*MP + k = reference row j*M + k
- *                for k < M, zero rows for M <= k < MP, MP = nfk_rq_coupling_final_padded_params(num_bins, tails)
- *   bias_packed: packed the same way, [d_t * MP]
+ *   a_hi/a_lo  : fp16 split pair (exponent a_exp) of the last hidden activation [n_rows, hidden_features]
+ *   wp_hi/wp_lo: fp16 split pair (exponent w_exp) of the PACKED final weight [d_t * MP, hidden_features]: row j*MP + k =
+ *                reference row j*M + k for k < M, zero rows for M <= k < MP, MP = nfk_rq_coupling_final_padded_params
+ *   bias_packed: fp32, packed the same way, [d_t * MP]
  * Writes y[n, t_cols[j]] for every transformed feature and adds the row's log|det| to lad_accum.  y may be x itself
- * (in place: the identity columns then need no copy); otherwise the caller fills the identity columns of y.  nfk_rq_coupling_final_supported says whether an
- * instance exists for (num_bins, tails, hidden_features, lda); otherwise use nfk_linear* + nfk_rqs_rows. */
+ * (in place: the identity columns then need no copy); otherwise the caller fills the identity columns of y.
+ * nfk_rq_coupling_final_supported says whether an instance exists for (num_bins, tails, hidden_features, lda); otherwise
+ * use nfk_linear* + nfk_rqs_rows. */
 int nfk_rq_coupling_final_supported(int32_t num_bins, int32_t linear_tails, int32_t hidden_features, int64_t lda);
 int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t linear_tails);
-int nfk_rq_coupling_final_tf32x3(const NfkSplineDesc* desc, int inverse, const float* a_hi, const float* a_lo, int64_t lda,
-                                 const float* wp_hi, const float* wp_lo, int64_t ldw, const float* bias_packed,
-                                 int32_t hidden_features, const float* x, int64_t ldx, const int32_t* t_cols, int32_t d_t,
-                                 float* y, int64_t ldy, float* lad_accum, int64_t n_rows, int32_t* flags, void* stream);
-/* Same kernel with the hidden activation given as plain fp32 `a` (split on chip after relu when relu_in), as written by
- * nfk_linear_tf32x3_a32 with Y != NULL: no (hi, lo) pair of the activations in HBM, half the activation operand traffic. */
-int nfk_rq_coupling_final_tf32x3_a32(const NfkSplineDesc* desc, int inverse, const float* a, int64_t lda, int relu_in,
-                                     const float* wp_hi, const float* wp_lo, int64_t ldw, const float* bias_packed,
-                                     int32_t hidden_features, const float* x, int64_t ldx, const int32_t* t_cols,
-                                     int32_t d_t, float* y, int64_t ldy, float* lad_accum, int64_t n_rows,
-                                     int32_t* flags, void* stream);
+int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int inverse, const void* a_hi, const void* a_lo, int64_t lda,
+                               int32_t a_exp, const void* wp_hi, const void* wp_lo, int64_t ldw, int32_t w_exp,
+                               const float* bias_packed, int32_t hidden_features, const float* x, int64_t ldx,
+                               const int32_t* t_cols, int32_t d_t, float* y, int64_t ldy, float* lad_accum, int64_t n_rows,
+                               int32_t* flags, void* stream);
 
 /* ---- row-wise elementwise transforms -------------------------------------------------------------------- */
 /* out[n, j] = x[n*ldx + cols[j]] (identity_split gather, coupling.py:82; Permutation._permute,

@@ -15,9 +15,10 @@ class _Config:
     param_chunk_mib = 64
     #: run the final conditioner layer and the spline as ONE tensor-core kernel when an instance exists
     fuse_coupling = True
-    #: hand the fused kernel the (hi, lo) split pair of the hidden activation (written by the last trunk layer) instead of
-    #: the fp32 activation it then splits on chip; kept for A/B measurements
-    fused_pair_input = False
+    #: power-of-two exponent applied to activations before they are split into fp16 (hi, lo) pairs for the tensor-core
+    #: dense layers: |a| * 2^exp must stay below 65000 (an overflow raises kernels.Float16RangeError) and |a| >= 2^-(3+exp)
+    #: keeps the full 22-bit precision; 6 covers 2e-3 .. 1000
+    activation_exp = 6
     #: rows per sub-block of a dense-layer chain: intermediates of a sub-block (split pairs, hidden activations) stay
     #: resident in the 126 MB L2 between consecutive kernels instead of round-tripping through HBM
     #: (measured r1: sub-blocks of 8-16 K rows are SLOWER -- 1-wave launches pay prologue/launch overhead -- so the default

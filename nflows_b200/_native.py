@@ -40,18 +40,14 @@ _SIGNATURES = {
                              c_int64, _P, _P]),
     "nfk_linear": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int32, c_int32, c_int, c_int,
                            _P]),
-    "nfk_linear_tf32x3_supported": (c_int, [c_int64, c_int64, c_int32]),
-    "nfk_linear_tf32x3": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int,
-                                  c_int, c_int64, c_int32, c_int32, _P]),
-    "nfk_linear_tf32x3_a32": (c_int, [_P, c_int64, c_int, _P, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int,
-                                      c_int, c_int64, c_int32, c_int32, _P]),
-    "nfk_split_tf32": (c_int, [_P, c_int64, _P, c_int32, c_int, _P, _P, c_int64, _P, c_int64, c_int64, _P]),
+    "nfk_linear_f16x3_supported": (c_int, [c_int64, c_int64, c_int32]),
+    "nfk_linear_f16x3": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64,
+                                 c_int32, c_int32, c_int, c_int, c_int64, c_int32, c_int32, _P, _P]),
+    "nfk_split_f16": (c_int, [_P, c_int64, c_int32, c_int, c_int32, _P, _P, c_int64, c_int64, _P, _P]),
     "nfk_rq_coupling_final_supported": (c_int, [c_int32, c_int32, c_int32, c_int64]),
     "nfk_rq_coupling_final_padded_params": (c_int32, [c_int32, c_int32]),
-    "nfk_rq_coupling_final_tf32x3": (c_int, [POINTER(NfkSplineDesc), c_int, _P, _P, c_int64, _P, _P, c_int64, _P, c_int32, _P,
-                                             c_int64, _P, c_int32, _P, c_int64, _P, c_int64, _P, _P]),
-    "nfk_rq_coupling_final_tf32x3_a32": (c_int, [POINTER(NfkSplineDesc), c_int, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int32,
-                                                 _P, c_int64, _P, c_int32, _P, c_int64, _P, c_int64, _P, _P]),
+    "nfk_rq_coupling_final_f16x3": (c_int, [POINTER(NfkSplineDesc), c_int, _P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P,
+                                            c_int32, _P, c_int64, _P, c_int32, _P, c_int64, _P, c_int64, _P, _P]),
     "nfk_gather_cols": (c_int, [_P, c_int64, _P, c_int32, _P, c_int64, c_int64, _P]),
     "nfk_actnorm": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, c_float, c_int64, c_int32, c_int, _P]),
     "nfk_add_const": (c_int, [_P, c_float, c_int64, _P]),
@@ -82,8 +78,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError here means header and library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.nfk_version() != 1:
-        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 1".format(lib.nfk_version()))
+    if lib.nfk_version() != 2:
+        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 2".format(lib.nfk_version()))
     _lib = lib
     return lib
 

@@ -2,29 +2,33 @@
 //
 //   Y = post(A W^T + b) + R           A: [n_rows, K]   W: [N, K] (nn.Linear layout)   fp32 accumulate in TMEM
 //
-// PyTorch's reference GEMM is true fp32 (allow_tf32=False), and a single TF32 pass misses the 1e-5 parity bar by
-// two orders of magnitude.  So every operand is carried as a split pair
-//   a = a_hi + a_lo,  a_hi = rna_tf32(a) (10-bit mantissa, stored in an fp32 container),  a_lo = a - a_hi (exact)
-// and each K-step issues three kind::tf32 MMAs into the same accumulator:  a_lo*w_hi + a_hi*w_lo + a_hi*w_hi
-// (the dropped a_lo*w_lo term is ~2^-22 relative).  Producers of activations write the split pair in their
-// epilogue, weights are split once when a module's parameters change.
+// PyTorch's reference GEMM is true fp32 (allow_tf32=False); one reduced-precision pass misses the 1e-5 parity bar by two
+// orders of magnitude.  So every operand is carried as a split pair of fp16 numbers
+//   v * 2^e = v_hi + v_lo,   v_hi = rn_fp16(v * 2^e),   v_lo = rn_fp16(v * 2^e - v_hi)        (22 mantissa bits)
+// with a per-tensor power-of-two scale 2^e that keeps v_lo out of the fp16 subnormals (weights: max |w| -> 2^14;
+// activations: a fixed exponent, overflow raises NFK_FLAG_F16_RANGE), and each K-step issues three kind::f16 MMAs into
+// the same accumulator:  a_lo*w_hi + a_hi*w_lo + a_hi*w_hi  (the dropped a_lo*w_lo term is ~2^-22 relative; fp16 x fp16
+// products are exact in the fp32 accumulator).  The epilogue multiplies by 2^-(e_a + e_w), exactly.
+// Why fp16 and not TF32 pairs (the first version of this kernel): the GPU runs these kernels AT ITS POWER CAP -- cuBLAS
+// sustains 643 TFLOP/s in TF32 but 1417 TFLOP/s in 16-bit on this box (scripts/tf32_peak.py) -- and the 3xTF32 kernels
+// already executed 630 TFLOP/s of TF32 MMAs.  fp16 pairs carry the same 22 bits at half the operand bytes (4 B per
+// element for the pair = one fp32), twice the K per MMA instruction and ~2.2x the flops per joule.
 //
 // Accumulation: the tensor core adds into its fp32 accumulator with round-toward-zero, so a long chain of MMAs
-// acquires a bias of ~0.5 ulp per instruction (measured here: 2e-5 relative after the 294 MMAs of K=784, the same
-// effect Ootomo & Yokota 2022 report for Ampere).  The accumulator in TMEM therefore only ever holds a PARTIAL sum
-// over DRAIN_SLABS_LINEAR K-slabs (24 MMAs); the epilogue warps drain it with tcgen05.ld and keep the running sum in
-// registers with round-to-nearest FADDs, while the issuer continues into the other TMEM buffer.
+// acquires a bias of ~0.5 ulp per instruction (measured: 2e-5 relative after 294 MMAs, the effect Ootomo & Yokota 2022
+// report for Ampere).  The accumulator in TMEM therefore only ever holds a PARTIAL sum over DRAIN_SLABS_LINEAR K-slabs
+// (12 MMAs); the epilogue warps drain it with tcgen05.ld and keep the running sum in registers with round-to-nearest
+// FADDs, while the issuer continues into the other TMEM buffer.
 //
 // Kernel shape (one persistent CTA per SM, 384 threads; setmaxnreg moves registers from warpgroup 0 to 1-2):
-//   warp 0   : TMA producer   -- cp.async.bulk.tensor 2-D boxes {32 k, 128 rows} / {32 k, BN rows}, SWIZZLE_128B,
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor 2-D boxes {32 k, 128 rows} / {32 k, BN rows} of fp16, SWIZZLE_64B,
 //                                out-of-bounds rows/columns zero-filled by the TMA unit (no padding anywhere)
-//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 8, K-major smem descriptors)
+//   warp 1   : TMEM allocator + tcgen05.mma issuer (UMMA 128 x BN x 16, K-major smem descriptors)
 //   warps 4-11: accumulate/epilogue -- warp w owns TMEM lanes [32(w%4), +32) and column half (w-4)/4 of the tile:
 //                                tcgen05.ld of each partial sum -> 128 running sums per thread in registers; at the end of
-//                                a tile bias / relu / residual -> global stores of the fp32 result and/or the split pair
+//                                a tile scale / relu / residual -> global stores of the fp32 result and/or the fp16 pair
 //                                consumed by the next layer
-//   smem ring: 4 stages x (A_hi, A_lo, W_hi, W_lo) of K = 16 = 4 x 48 KB (three loads in flight while one slab is
-//   consumed: the 2 x 96 KB ring of the first version was latency-bound);  TMEM: 2 partial accumulators x 256 columns.
+//   smem ring: 4 stages x (A_hi, A_lo, W_hi, W_lo) of K = 32 = 4 x 48 KB;  TMEM: 2 partial accumulators x 256 columns.
 #include <stdlib.h>
 
 #include <mutex>
@@ -38,8 +42,13 @@ struct Params {
     const float* bias;       // [N] or null
     const float* residual;   // [n_rows, ldr] or null
     float* y;                // fp32 result or null
-    float* y_hi;             // split pair of pre(y) for the next layer, or null
-    float* y_lo;
+    __half* y_hi;            // fp16 split pair of pre(y) * out_scale for the next layer, or null
+    __half* y_lo;
+    int32_t* flags;          // NFK_FLAG_F16_RANGE when a pair output leaves the fp16 range
+    float acc_scale;         // 2^(e_a + e_w): the accumulators hold (A W^T) * acc_scale
+    float inv_acc_scale;
+    float out_scale;         // 2^e of the pair output
+    int split_n;             // pair output for columns < split_n only
     int64_t ldr, ldy, lds;
     int64_t n_rows;
     int K, N, BN;
@@ -47,7 +56,6 @@ struct Params {
     int split_relu;          // relu applied before splitting (the next layer consumes relu(y))
     int num_m_tiles, num_n_tiles;
     int n_inner;             // tile schedule, see tile_of()
-    int relu_in;             // A32 kernels: relu applied to A while it is split in shared memory
 };
 
 // Tile schedule of a persistent CTA.  With at least one 128-row block per CTA ("n_inner") a CTA walks all column tiles of
@@ -72,13 +80,9 @@ __device__ __forceinline__ bool tile_of(const int it, const int n_inner, const i
     return t < units * num_n;
 }
 
-// A32 = the A operand arrives as plain fp32: the TMA producer lands the raw K-slab in the "hi" half of the stage and the
-// two otherwise idle warps of warpgroup 0 split it IN PLACE (hi = rna_tf32(pre(a)) over the raw bytes, lo = pre(a) - hi
-// into the "lo" half; elementwise, so the TMA swizzle pattern is preserved) before the MMA thread may read the stage.
-// Producers then write ONE fp32 tensor instead of a (hi, lo) pair and the stand-alone split passes disappear.
-template <int CL, bool A32>
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
-linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -87,16 +91,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     const uint32_t bars = smem_base + STAGES * STAGE_BYTES;                // 8-byte mbarriers
     const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
     const uint32_t bar_tfull = bars + 16 * STAGES, bar_tempty = bars + 16 * STAGES + 16;
-    const uint32_t bar_split = bars + 16 * STAGES + 32;                    // A32: stage has been split by warps 2-3
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 24 * STAGES + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (p.K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); mbar_init(bar_split + 8 * s, 2);
-        }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -115,7 +116,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 0) {
         // ================================================= TMA producer
         if (lane == 0) {
-            const uint32_t tx_bytes = (A32 ? 1u : 2u) * A_BYTES + 2u * (uint32_t)p.BN * BK * 4u;
+            const uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)p.BN * ROW_BYTES;
             int stage = 0; uint32_t phase = 0;
             int tm, tn;
             const int wrows = p.BN / CL;                                   // weight rows this CTA fetches per slab
@@ -128,7 +129,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
                     mbar_expect_tx(full, tx_bytes);
                     tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
-                    if (!A32) tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
+                    tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
                     if (CL == 1) {
                         tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n0);
                         tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n0);
@@ -163,7 +164,6 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                         int st = stage; uint32_t ph = phase;
                         for (int j = 0; j < pair; ++j) {
                             mbar_wait(bar_full + 8 * st, ph);              // TMA bytes have landed
-                            if (A32) mbar_wait(bar_split + 8 * st, ph);     // ... and A has been split in place
                             if (++st == STAGES) { st = 0; ph ^= 1; }
                         }
                         tc_fence_after();
@@ -173,10 +173,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                             const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
                             const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 8; ++kk) {          // UMMA K = 8 tf32 = 32 bytes = +2 in descriptor units
+                            for (int kk = 0; kk < BK / 16; ++kk) {         // UMMA K = 16 fp16 = 32 bytes = +2 in descriptor units
                                 const uint64_t adv = (uint64_t)(kk * 2);
-                                if (leader) umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
-                                if (leader) umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                                if (leader) umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
+                                if (leader) umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                             }
                             if (++st == STAGES) st = 0;
                         }
@@ -184,9 +184,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                             const uint32_t sa = smem_base + stage * STAGE_BYTES;
                             const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 8; ++kk) {
+                            for (int kk = 0; kk < BK / 16; ++kk) {
                                 const uint64_t adv = (uint64_t)(kk * 2);
-                                if (leader) umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                                if (leader) umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                             }
                             if (!leader) {} else if (CL == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot when the MMAs retire
                             else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // ... in every CTA of the cluster
@@ -198,35 +198,6 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                 }
             }
         }
-    } else if (A32) {
-        // ================================================= warps 2-3: split the raw A slab of every stage in place
-        const int t = (warp - 2) * 32 + lane;                                 // 64 threads x 8 float4 = one 8 KB slab
-        int stage = 0; uint32_t phase = 0;
-        int tm, tn;
-        for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
-            for (int ks = 0; ks < num_k; ++ks) {
-                mbar_wait(bar_full + 8 * stage, phase);
-                float4* hi = reinterpret_cast<float4*>(smem_gen + stage * STAGE_BYTES);
-                float4* lo = reinterpret_cast<float4*>(smem_gen + stage * STAGE_BYTES + A_BYTES);
-#pragma unroll
-                for (int b = 0; b < A_BYTES / 16 / 64; b += 4) {
-                    float4 v[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) v[i] = hi[t + 64 * (b + i)];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (p.relu_in) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
-                        const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
-                        hi[t + 64 * (b + i)] = h;
-                        lo[t + 64 * (b + i)] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_split + 8 * stage);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
-        }
     }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
@@ -235,8 +206,9 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
         const int half = (warp - 4) >> 2;         // column half of the tile
         int acc = 0; uint32_t acc_phase = 0;
         const bool vec_y = p.y && (p.ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-        const bool vec_s = p.y_hi && (p.lds % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.y_hi) & 15) == 0) &&
+        const bool vec_s = p.y_hi && (p.lds % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.y_hi) & 15) == 0) &&
                            ((reinterpret_cast<uintptr_t>(p.y_lo) & 15) == 0);
+        int flag = 0;
         const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         const bool vec_b = !p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
         int tm, tn;
@@ -284,6 +256,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     }
                 }
             }
+            // the accumulators hold (A W^T) * acc_scale (operands are power-of-two scaled fp16 pairs): the running sums live
+            // in that domain (exact), the tile epilogue scales back
+#pragma unroll
+            for (int c = 0; c < HALF; ++c) sum[c] *= p.acc_scale;
             for (int g = 0; g < num_groups; ++g) {
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
                 tc_fence_after();
@@ -318,7 +294,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float x = sum[c + j];                              // bias (and a foldable residual) already included
+                        float x = sum[c + j] * p.inv_acc_scale;            // bias (and a foldable residual) already included
                         if (p.relu_out) x = fmaxf(x, 0.0f);
                         v[j] = x;
                     }
@@ -347,31 +323,30 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
                             for (int j = 0; j < 16; ++j) if (col0 + j < p.N) yp[j] = v[j];
                         }
                     }
-                    if (p.y_hi) {
-                        float hi[16], lo[16];
+                    if (p.y_hi && col0 < p.split_n) {
+                        __half hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const float x = p.split_relu ? fmaxf(v[j], 0.0f) : v[j];
-                            hi[j] = tf32_hi(x);
-                            lo[j] = x - hi[j];
+                            split_f16(x, p.out_scale, hi[j], lo[j], flag);
                         }
-                        float* hp = p.y_hi + row * p.lds + col0;
-                        float* lp = p.y_lo + row * p.lds + col0;
-                        if (vec_s && full16) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                *reinterpret_cast<float4*>(hp + 4 * j) = make_float4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                                *reinterpret_cast<float4*>(lp + 4 * j) = make_float4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                            }
+                        __half* hp = p.y_hi + row * p.lds + col0;
+                        __half* lp = p.y_lo + row * p.lds + col0;
+                        if (vec_s && col0 + 16 <= p.split_n && full16) {
+                            const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+                            const uint4* l4 = reinterpret_cast<const uint4*>(lo);
+                            reinterpret_cast<uint4*>(hp)[0] = h4[0]; reinterpret_cast<uint4*>(hp)[1] = h4[1];
+                            reinterpret_cast<uint4*>(lp)[0] = l4[0]; reinterpret_cast<uint4*>(lp)[1] = l4[1];
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N) { hp[j] = hi[j]; lp[j] = lo[j]; }
+                            for (int j = 0; j < 16; ++j) if (col0 + j < p.N && col0 + j < p.split_n) { hp[j] = hi[j]; lp[j] = lo[j]; }
                         }
                     }
                 }
             }
             __syncwarp();
         }
+        if (flag && p.flags) atomicOr(p.flags, flag);
     }
 
     tc_fence_before();
@@ -379,13 +354,13 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// ---------------------------------------------------------------- fp32 -> (hi, lo) split, optional column gather / relu
-// HBM-bound: 4 B read + 8 B written per element (+ 4 B for the optional identity copy).  One warp per row chunk; the
-// un-gathered case moves 16 bytes per thread per access.
-__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ldx,
-                                                         const int32_t* __restrict__ cols, int n_cols, int relu,
-                                                         float* __restrict__ hi, float* __restrict__ lo, int64_t ldo,
-                                                         float* __restrict__ copy_dst, int64_t ldc, int64_t n_rows, int vec4) {
+// ---------------------------------------------------------------- fp32 -> fp16 (hi, lo) split pair, optional relu
+// HBM-bound: 4 B read + 4 B written per element.  Used for weights (once per parameter update), for tensors entering a
+// tensor-core chain from outside and for the transformed half of a coupling output.
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, int64_t ldx, int n_cols, int relu,
+                                                        float scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                                                        int64_t ldo, int64_t n_rows, int vec4, int32_t* flags) {
+    int flag = 0;
     if (vec4) {
         const int n4 = n_cols >> 2;
         const int64_t total = n_rows * n4;
@@ -394,24 +369,26 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
             const int j = (int)(i - r * n4) * 4;
             float4 v = __ldcs(reinterpret_cast<const float4*>(x + r * ldx + j));
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            *reinterpret_cast<float4*>(hi + r * ldo + j) = h;
-            *reinterpret_cast<float4*>(lo + r * ldo + j) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            __half h[4], l[4];
+            split_f16(v.x, scale, h[0], l[0], flag); split_f16(v.y, scale, h[1], l[1], flag);
+            split_f16(v.z, scale, h[2], l[2], flag); split_f16(v.w, scale, h[3], l[3], flag);
+            *reinterpret_cast<uint2*>(hi + r * ldo + j) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(lo + r * ldo + j) = *reinterpret_cast<const uint2*>(l);
         }
-        return;
+    } else {
+        const int64_t total = n_rows * n_cols;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = i / n_cols;
+            const int j = (int)(i - r * n_cols);
+            float v = x[r * ldx + j];
+            if (relu) v = fmaxf(v, 0.0f);
+            __half h, l;
+            split_f16(v, scale, h, l, flag);
+            hi[r * ldo + j] = h;
+            lo[r * ldo + j] = l;
+        }
     }
-    const int64_t total = n_rows * n_cols;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / n_cols;
-        const int j = (int)(i - r * n_cols);
-        const int c = cols ? __ldg(cols + j) : j;
-        float v = x[r * ldx + c];
-        if (copy_dst) copy_dst[r * ldc + c] = v;          // bit-exact pass-through of the identity columns
-        if (relu) v = fmaxf(v, 0.0f);
-        const float h = tf32_hi(v);
-        hi[r * ldo + j] = h;
-        lo[r * ldo + j] = v - h;
-    }
+    if (flag && flags) atomicOr(flags, flag);
 }
 
 // ---------------------------------------------------------------- host side
@@ -432,14 +409,14 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int K, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t ld, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, ROW_BYTES == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -462,43 +439,49 @@ int sm_count() {
 
 using namespace nfk;
 
-extern "C" int nfk_split_tf32(const float* x, int64_t ldx, const int32_t* cols, int32_t n_cols, int relu, float* hi,
-                              float* lo, int64_t ldo, float* copy_dst, int64_t ldc, int64_t n_rows, void* stream) {
-    NFK_REQUIRE(n_rows >= 0 && n_cols >= 0, "bad sizes");
+static bool pow2_exp_ok(int e) { return e >= -60 && e <= 60; }
+
+extern "C" int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int relu, int32_t scale_exp, void* hi, void* lo,
+                             int64_t ldo, int64_t n_rows, int32_t* flags, void* stream) {
+    NFK_REQUIRE(n_rows >= 0 && n_cols >= 0 && pow2_exp_ok(scale_exp), "bad sizes");
     if (n_rows == 0 || n_cols == 0) return NFK_OK;
     NFK_REQUIRE(x && hi && lo, "NULL pointer");
-    const int vec4 = (!cols && !copy_dst && n_cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && aligned16(hi) &&
-                      aligned16(lo)) ? 1 : 0;
+    const int vec4 = (n_cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(lo) & 7) == 0) ? 1 : 0;
     int64_t blocks = (n_rows * (vec4 ? n_cols / 4 : n_cols) + 255) / 256;
     int grid = (int)(blocks > 148 * 32 ? 148 * 32 : blocks);
-    tc::split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, cols, n_cols, relu, hi, lo, ldo, copy_dst, ldc, n_rows,
-                                                                  vec4);
-    return check_launch("split_tf32_kernel");
+    tc::split_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, n_cols, relu, ldexpf(1.0f, scale_exp), (__half*)hi, (__half*)lo,
+                                                                 ldo, n_rows, vec4, flags);
+    return check_launch("split_f16_kernel");
 }
 
-extern "C" int nfk_linear_tf32x3_supported(int64_t lda, int64_t ldw, int32_t in_features) {
-    return (in_features >= 4 && in_features % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0) ? 1 : 0;
+// fp16 rows must start on 16-byte boundaries for TMA: leading dimensions and K multiples of 8
+extern "C" int nfk_linear_f16x3_supported(int64_t lda, int64_t ldw, int32_t in_features) {
+    return (in_features >= 8 && in_features % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0) ? 1 : 0;
 }
 
-// a_lo == nullptr selects the A32 kernels: `a_hi` is then the plain fp32 activation, split (after an optional relu) on chip
-static int launch_linear(const float* a_hi, const float* a_lo, int relu_in, int64_t lda, const float* w_hi, const float* w_lo,
-                         int64_t ldw, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
-                         float* y_hi, float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
-                         int32_t in_features, int32_t out_features, void* stream) {
-    const bool a32 = a_lo == nullptr;
+extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t lda, int32_t a_exp, const void* w_hi_,
+                                const void* w_lo_, int64_t ldw, int32_t w_exp, const float* bias, const float* R, int64_t ldr,
+                                float* Y, int64_t ldy, void* y_hi_, void* y_lo_, int64_t lds, int32_t y_exp, int32_t split_cols,
+                                int relu_out, int split_relu, int64_t n_rows, int32_t in_features, int32_t out_features,
+                                int32_t* flags, void* stream) {
+    const __half* a_hi = (const __half*)a_hi_; const __half* a_lo = (const __half*)a_lo_;
+    const __half* w_hi = (const __half*)w_hi_; const __half* w_lo = (const __half*)w_lo_;
+    __half* y_hi = (__half*)y_hi_; __half* y_lo = (__half*)y_lo_;
     NFK_REQUIRE(n_rows >= 0 && in_features >= 1 && out_features >= 1, "bad sizes");
     if (n_rows == 0) return NFK_OK;
-    NFK_REQUIRE(a_hi && w_hi && w_lo, "NULL operand pointer");
+    NFK_REQUIRE(a_hi && a_lo && w_hi && w_lo, "NULL operand pointer");
     NFK_REQUIRE(Y || (y_hi && y_lo), "no output requested");
     NFK_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "y_hi and y_lo must be given together");
-    NFK_REQUIRE(nfk_linear_tf32x3_supported(lda, ldw, in_features), "tf32x3 path needs in_features, lda, ldw multiples of 4");
+    NFK_REQUIRE(nfk_linear_f16x3_supported(lda, ldw, in_features), "f16x3 path needs in_features, lda, ldw multiples of 8");
     NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(w_hi) && aligned16(w_lo), "operands must be 16-byte aligned");
     NFK_REQUIRE(n_rows < (1ll << 31), "n_rows too large for one launch");
-    NFK_REQUIRE(!a32 || (Y != a_hi && y_hi != a_hi && y_lo != a_hi), "outputs must not alias the input");
+    NFK_REQUIRE(pow2_exp_ok(a_exp) && pow2_exp_ok(w_exp) && pow2_exp_ok(y_exp), "scale exponent out of range");
 
     tc::Params p;
-    p.relu_in = relu_in;
-    p.bias = bias; p.residual = R; p.y = Y; p.y_hi = y_hi; p.y_lo = y_lo;
+    p.bias = bias; p.residual = R; p.y = Y; p.y_hi = y_hi; p.y_lo = y_lo; p.flags = flags;
+    p.acc_scale = ldexpf(1.0f, a_exp + w_exp); p.inv_acc_scale = ldexpf(1.0f, -(a_exp + w_exp)); p.out_scale = ldexpf(1.0f, y_exp);
+    p.split_n = split_cols > 0 ? split_cols : out_features;
     p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
     p.relu_out = relu_out; p.split_relu = split_relu;
     p.num_n_tiles = (out_features + tc::BN_MAX - 1) / tc::BN_MAX;
@@ -517,24 +500,20 @@ static int launch_linear(const float* a_hi, const float* a_lo, int relu_in, int6
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     int rc;
     if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, in_features, lda, tc::BM))) return rc;
-    if ((rc = tc::make_map(&ma_lo, a32 ? a_hi : a_lo, n_rows, in_features, lda, tc::BM))) return rc;
+    if ((rc = tc::make_map(&ma_lo, a_lo, n_rows, in_features, lda, tc::BM))) return rc;
     if ((rc = tc::make_map(&mw_hi, w_hi, out_features, in_features, ldw, bn / CL))) return rc;
     if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn / CL))) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tc::linear_tf32x3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+            e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::SMEM_BYTES, cudaGetErrorString(e));
         attr_set = true;
     }
     const int units = (p.num_m_tiles + CL - 1) / CL;
-    p.n_inner = 0;   // measured r1: walking the column tiles of a row block back to back did not help (L2-feed-, not HBM-bound)
+    p.n_inner = 0;   // measured r1: walking the column tiles of a row block back to back did not help
     const int work = units * p.num_n_tiles;
     const int max_clusters = tc::sm_count() / CL;
     cudaLaunchConfig_t cfg = {};
@@ -547,30 +526,8 @@ static int launch_linear(const float* a_hi, const float* a_lo, int relu_in, int6
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le;
-    if (a32)
-        le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<2, true>, ma_hi, ma_lo, mw_hi, mw_lo, p)
-                       : cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<1, true>, ma_hi, ma_lo, mw_hi, mw_lo, p);
-    else
-        le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<2, false>, ma_hi, ma_lo, mw_hi, mw_lo, p)
-                       : cudaLaunchKernelEx(&cfg, tc::linear_tf32x3_kernel<1, false>, ma_hi, ma_lo, mw_hi, mw_lo, p);
-    if (le != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(linear_tf32x3_kernel, cluster %d): %s", CL, cudaGetErrorString(le));
-    return check_launch("linear_tf32x3_kernel");
-}
-
-extern "C" int nfk_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t lda, const float* w_hi, const float* w_lo,
-                                 int64_t ldw, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
-                                 float* y_hi, float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
-                                 int32_t in_features, int32_t out_features, void* stream) {
-    NFK_REQUIRE(a_lo, "NULL operand pointer");
-    return launch_linear(a_hi, a_lo, 0, lda, w_hi, w_lo, ldw, bias, R, ldr, Y, ldy, y_hi, y_lo, lds, relu_out, split_relu, n_rows,
-                         in_features, out_features, stream);
-}
-
-extern "C" int nfk_linear_tf32x3_a32(const float* a, int64_t lda, int relu_in, const float* w_hi, const float* w_lo, int64_t ldw,
-                                     const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy, float* y_hi,
-                                     float* y_lo, int64_t lds, int relu_out, int split_relu, int64_t n_rows,
-                                     int32_t in_features, int32_t out_features, void* stream) {
-    return launch_linear(a, nullptr, relu_in, lda, w_hi, w_lo, ldw, bias, R, ldr, Y, ldy, y_hi, y_lo, lds, relu_out, split_relu,
-                         n_rows, in_features, out_features, stream);
+    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, p)
+                               : cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    if (le != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(linear_f16x3_kernel, cluster %d): %s", CL, cudaGetErrorString(le));
+    return check_launch("linear_f16x3_kernel");
 }

@@ -31,7 +31,8 @@ struct FusedParams {
     int d_t;
     int num_m_tiles, num_n_tiles;
     int inverse;
-    int relu_in;            // A32 kernels: relu applied to the hidden activation while it is split on chip
+    float acc_scale;        // 2^(e_a + e_w): the accumulators hold (A Wp^T) * acc_scale (fp16 pairs are power-of-two scaled)
+    float inv_acc_scale;
     SplineParams sp;
 };
 
@@ -188,10 +189,7 @@ __device__ __forceinline__ void rqs_eval_multi(const SplineParams& p, bool inver
 // MODE 3: the same two CTAs as a tcgen05 CTA PAIR (cta_group::2): the leader issues ONE 256 x BN x 8 MMA for both SMs, each
 //         CTA keeps only its half of the weight tile (no multicast copy), so shared-memory operand reads per SM drop from
 //         (128 + BN) to (128 + BN/2) rows per MMA and the stage ring deepens from 4 to 6 slabs in the same 192 KB.
-// A32: the hidden activation arrives as plain fp32 and is split into (hi, lo) in shared memory by warps 2-3 (as in
-// nfk_linear_tc.cu) -- the activation half of the L2 -> SM operand stream shrinks from 16 to 8 KB per K-slab and the last
-// trunk layer writes one tensor instead of two.  Not combined with MODE 3.
-template <int NB, bool TAILS, int MODE, bool A32>
+template <int NB, bool TAILS, int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -199,7 +197,6 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     using Cfg = FusedCfg<NB, TAILS>;
     constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HALF_COLS, BN = Cfg::BN, TILE = Cfg::TILE_COLS;
     constexpr bool PAIR = MODE == 3;
-    static_assert(!(PAIR && A32), "on-chip split is not implemented for CTA pairs");
     constexpr int CL = MODE == 1 ? 1 : 2;
     constexpr int NST = PAIR ? PAIR_STAGES : STAGES;                 // slabs in the shared-memory ring
     constexpr int SB = PAIR ? PAIR_STAGE_BYTES : STAGE_BYTES;        // bytes per slab: [A hi | A lo | W hi | W lo]
@@ -212,8 +209,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * NST;
     const uint32_t bar_tfull = bars + 16 * NST, bar_tempty = bars + 16 * NST + 16;
-    const uint32_t bar_split = bars + 16 * NST + 32;                 // A32: warps 2-3 have split the slab's activation half
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 24 * NST + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * NST + 32);
     float* s_lad = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);       // [EWG-1][128] partial log|det|
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -223,9 +219,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     if (threadIdx.x == 0) {
         // MODE 2: both CTAs' MMA threads release a slot (the peer multicasts into it); MODE 3: the leader's commit reaches
         // both CTAs' barriers, and the leader's accumulator barrier collects the epilogue warps of BOTH CTAs
-        for (int s = 0; s < NST; ++s) {
-            mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, MODE == 2 ? 2 : 1); mbar_init(bar_split + 8 * s, 2);
-        }
+        for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, MODE == 2 ? 2 : 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * 4 * EWG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -247,8 +241,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             if (lane == 0) {
                 // bytes counted on the slab's barrier: MODE 1/2 everything landing in THIS CTA's slab; MODE 3 both CTAs' loads
                 // (A of both + both halves of W) on the leader's barrier
-                constexpr uint32_t tx_bytes = PAIR ? 2u * (2u * A_BYTES + (uint32_t)BN * BK * 4u)
-                                                   : (A32 ? 1u : 2u) * A_BYTES + 2u * (uint32_t)BN * BK * 4u;
+                constexpr uint32_t tx_bytes = PAIR ? 2u * (2u * A_BYTES + (uint32_t)BN * ROW_BYTES)
+                                                   : 2u * A_BYTES + 2u * (uint32_t)BN * ROW_BYTES;
                 constexpr int WROWS = BN / CL;                                             // weight rows this CTA fetches
                 int stage = 0; uint32_t phase = 0;
                 for (int mb = first_block; mb < num_blocks; mb += block_step) {
@@ -270,7 +264,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                             }
                             mbar_expect_tx(full, tx_bytes);
                             tma_load_2d(sa, &map_a_hi, full, ks * BK, m * BM);
-                            if (!A32) tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m * BM);
+                            tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m * BM);
                             if (CL == 1) {
                                 tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n * TILE);
                                 tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n * TILE);
@@ -295,7 +289,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 int acc = 0; uint32_t acc_phase = 0;
                 auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
                     if (!leader) return;
-                    if (PAIR) umma_tf32_pair(d, a, b, idesc, accumulate); else umma_tf32(d, a, b, idesc, accumulate);
+                    if (PAIR) umma_f16_pair(d, a, b, idesc, accumulate); else umma_f16(d, a, b, idesc, accumulate);
                 };
                 for (int mb = first_block; mb < num_blocks; mb += block_step) {
                     for (int n = 0; n < p.num_n_tiles; ++n) {
@@ -311,7 +305,6 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                                 int st = stage; uint32_t ph = phase;
                                 for (int j = 0; j < pair; ++j) {
                                     mbar_wait(bar_full + 8 * st, ph);
-                                    if (A32) mbar_wait(bar_split + 8 * st, ph);
                                     if (++st == NST) { st = 0; ph ^= 1; }
                                 }
                                 tc_fence_after();
@@ -321,7 +314,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                                     const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
                                     const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + WLO);
 #pragma unroll
-                                    for (int kk = 0; kk < BK / 8; ++kk) {
+                                    for (int kk = 0; kk < BK / 16; ++kk) {
                                         const uint64_t adv = (uint64_t)(kk * 2);
                                         mma(d_tmem, a_lo + adv, w_hi + adv, (j0 | j | kk) != 0);
                                         mma(d_tmem, a_hi + adv, w_lo + adv, 1);
@@ -332,7 +325,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                                     const uint32_t sa = smem_base + stage * SB;
                                     const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
 #pragma unroll
-                                    for (int kk = 0; kk < BK / 8; ++kk) {
+                                    for (int kk = 0; kk < BK / 16; ++kk) {
                                         const uint64_t adv = (uint64_t)(kk * 2);
                                         mma(d_tmem, a_hi + adv, w_hi + adv, 1);
                                     }
@@ -348,36 +341,6 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                             else umma_commit(bar_tfull + 8 * acc);
                             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         }
-                    }
-                }
-            }
-        } else if (A32 && warp >= 2) {
-            // ================================================= warps 2-3: split the raw activation slab of every stage in place
-            const int t = (warp - 2) * 32 + lane;                             // 64 threads x 8 float4 = one 8 KB slab
-            int stage = 0; uint32_t phase = 0;
-            for (int mb = first_block; mb < num_blocks; mb += block_step) {
-                for (int n = 0; n < p.num_n_tiles; ++n) {
-                    for (int ks = 0; ks < num_k; ++ks) {
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        float4* hi = reinterpret_cast<float4*>(smem_gen + stage * SB);
-                        float4* lo = reinterpret_cast<float4*>(smem_gen + stage * SB + A_BYTES);
-#pragma unroll
-                        for (int b = 0; b < A_BYTES / 16 / 64; b += 4) {
-                            float4 v[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) v[i] = hi[t + 64 * (b + i)];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                if (p.relu_in) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }
-                                const float4 h = make_float4(tf32_hi(v[i].x), tf32_hi(v[i].y), tf32_hi(v[i].z), tf32_hi(v[i].w));
-                                hi[t + 64 * (b + i)] = h;
-                                lo[t + 64 * (b + i)] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
-                            }
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_split + 8 * stage);
-                        if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -412,7 +375,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
 #pragma unroll
                 for (int c = 0; c < HC; c += 4) {
                     const float4 b4 = (j0 + c / MP < p.d_t) ? __ldg(bias_tile + (c >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    sum[c] = b4.x; sum[c + 1] = b4.y; sum[c + 2] = b4.z; sum[c + 3] = b4.w;
+                    sum[c] = b4.x * p.acc_scale; sum[c + 1] = b4.y * p.acc_scale;      // the sums live in the accumulators'
+                    sum[c + 2] = b4.z * p.acc_scale; sum[c + 3] = b4.w * p.acc_scale;  // power-of-two scaled domain (exact)
                 }
                 for (int ks = 0; ks < num_groups; ++ks) {
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
@@ -448,6 +412,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
                 // ---- spline on the FPT features held in registers, all features advanced together (ILP = FPT)
+#pragma unroll
+                for (int c = 0; c < HC; ++c) sum[c] *= p.inv_acc_scale;
                 {
                     float yy[FPT], ll[FPT];
                     rqs_eval_multi<NB, TAILS, FPT, MP>(p.sp, p.inverse != 0, xin, sum, yy, ll, flag);
@@ -494,8 +460,8 @@ static int cluster_mode() {
     return mode;
 }
 
-template <int NB, bool TAILS, int MODE, bool A32>
-static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo, int64_t ldw,
+template <int NB, bool TAILS, int MODE>
+static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const __half* w_hi, const __half* w_lo, int64_t ldw,
                            FusedParams& p, cudaStream_t st) {
     using Cfg = FusedCfg<NB, TAILS>;
     constexpr int CL = MODE == 1 ? 1 : 2;
@@ -508,7 +474,7 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     constexpr int smem = SMEM_BYTES + 512 * EWG;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, MODE, A32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
         attr_set = true;
     }
@@ -524,23 +490,18 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, MODE, A32>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, MODE>, ma_hi, ma_lo, mw_hi, mw_lo, p);
     if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(rq_coupling_final_kernel, cluster %d): %s", CL, cudaGetErrorString(e));
     return check_launch("rq_coupling_final_kernel");
 }
 
 template <int NB, bool TAILS>
-static int launch_fused(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const float* w_hi, const float* w_lo, int64_t ldw,
-                        FusedParams& p, cudaStream_t st, bool a32) {
-    const int mode = cluster_mode();
-    if (a32) {
-        if (mode == 1) return launch_fused_cl<NB, TAILS, 1, true>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
-        return launch_fused_cl<NB, TAILS, 2, true>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
-    }
-    switch (mode) {
-        case 1: return launch_fused_cl<NB, TAILS, 1, false>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
-        case 2: return launch_fused_cl<NB, TAILS, 2, false>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
-        default: return launch_fused_cl<NB, TAILS, 3, false>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+static int launch_fused(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const __half* w_hi, const __half* w_lo, int64_t ldw,
+                        FusedParams& p, cudaStream_t st) {
+    switch (cluster_mode()) {
+        case 1: return launch_fused_cl<NB, TAILS, 1>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+        case 2: return launch_fused_cl<NB, TAILS, 2>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+        default: return launch_fused_cl<NB, TAILS, 3>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
     }
 }
 
@@ -551,7 +512,7 @@ using namespace nfk;
 
 extern "C" int nfk_rq_coupling_final_supported(int32_t num_bins, int32_t linear_tails, int32_t hidden_features, int64_t lda) {
     const bool bins_ok = (num_bins == 8 || num_bins == 10 || num_bins == 4 || num_bins == 16);
-    return (bins_ok && hidden_features >= 4 && hidden_features % 4 == 0 && lda % 4 == 0) ? 1 : 0;
+    return (bins_ok && hidden_features >= 8 && hidden_features % 8 == 0 && lda % 8 == 0) ? 1 : 0;
 }
 
 extern "C" int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t linear_tails) {
@@ -559,35 +520,36 @@ extern "C" int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t
     return (m + 7) / 8 * 8;
 }
 
-// a_lo == nullptr: `a_hi` is the plain fp32 activation (split on chip after an optional relu)
-static int fused_entry(const NfkSplineDesc* desc, int inverse, const float* a_hi, const float* a_lo, int relu_in,
-                       int64_t lda, const float* wp_hi, const float* wp_lo, int64_t ldw,
-                       const float* bias_packed, int32_t hidden_features, const float* x, int64_t ldx,
-                       const int32_t* t_cols, int32_t d_t, float* y, int64_t ldy, float* lad_accum,
-                       int64_t n_rows, int32_t* flags, void* stream) {
-    const bool a32 = a_lo == nullptr;
+extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int inverse, const void* a_hi_, const void* a_lo_,
+                                          int64_t lda, int32_t a_exp, const void* wp_hi_, const void* wp_lo_, int64_t ldw,
+                                          int32_t w_exp, const float* bias_packed, int32_t hidden_features, const float* x,
+                                          int64_t ldx, const int32_t* t_cols, int32_t d_t, float* y, int64_t ldy,
+                                          float* lad_accum, int64_t n_rows, int32_t* flags, void* stream) {
+    const __half* a_hi = (const __half*)a_hi_; const __half* a_lo = (const __half*)a_lo_;
+    const __half* wp_hi = (const __half*)wp_hi_; const __half* wp_lo = (const __half*)wp_lo_;
     tc::FusedParams p;
     int rc = make_spline_params(desc, &p.sp);
     if (rc) return rc;
     NFK_REQUIRE(n_rows >= 0 && d_t >= 1 && hidden_features >= 1, "bad sizes");
     if (n_rows == 0) return NFK_OK;
-    NFK_REQUIRE(a_hi && wp_hi && wp_lo && bias_packed && x && t_cols && y, "NULL pointer");
-    NFK_REQUIRE(nfk_rq_coupling_final_supported(desc->num_bins, desc->linear_tails, hidden_features, lda) && ldw % 4 == 0,
+    NFK_REQUIRE(a_hi && a_lo && wp_hi && wp_lo && bias_packed && x && t_cols && y, "NULL pointer");
+    NFK_REQUIRE(nfk_rq_coupling_final_supported(desc->num_bins, desc->linear_tails, hidden_features, lda) && ldw % 8 == 0,
                 "fused coupling kernel does not take num_bins=%d hidden=%d", desc->num_bins, hidden_features);
     NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(wp_hi) && aligned16(wp_lo), "operands must be 16-byte aligned");
     NFK_REQUIRE(n_rows < (1ll << 31), "n_rows too large for one launch");
+    NFK_REQUIRE(a_exp + w_exp >= -60 && a_exp + w_exp <= 60, "scale exponent out of range");
     p.bias = bias_packed; p.x = x; p.y = y; p.t_cols = t_cols; p.lad_accum = lad_accum; p.flags = flags;
     p.ldx = ldx; p.ldy = ldy; p.n_rows = n_rows; p.K = hidden_features; p.d_t = d_t; p.inverse = inverse;
-    p.relu_in = relu_in;
+    p.acc_scale = ldexpf(1.0f, a_exp + w_exp); p.inv_acc_scale = ldexpf(1.0f, -(a_exp + w_exp));
     p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
     CUtensorMap ma_hi, ma_lo;
     if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, hidden_features, lda, tc::BM))) return rc;
-    if ((rc = tc::make_map(&ma_lo, a32 ? a_hi : a_lo, n_rows, hidden_features, lda, tc::BM))) return rc;
+    if ((rc = tc::make_map(&ma_lo, a_lo, n_rows, hidden_features, lda, tc::BM))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const bool tails = desc->linear_tails != 0;
 #define NFK_FUSED(NB)                                                                                       \
-    return tails ? tc::launch_fused<NB, true>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st, a32)                   \
-                 : tc::launch_fused<NB, false>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st, a32)
+    return tails ? tc::launch_fused<NB, true>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st)                        \
+                 : tc::launch_fused<NB, false>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st)
     switch (desc->num_bins) {
         case 4: NFK_FUSED(4);
         case 8: NFK_FUSED(8);
@@ -596,23 +558,4 @@ static int fused_entry(const NfkSplineDesc* desc, int inverse, const float* a_hi
     }
 #undef NFK_FUSED
     return fail(NFK_E_UNSUPPORTED, "num_bins=%d has no fused kernel instance", desc->num_bins);
-}
-
-extern "C" int nfk_rq_coupling_final_tf32x3(const NfkSplineDesc* desc, int inverse, const float* a_hi, const float* a_lo,
-                                            int64_t lda, const float* wp_hi, const float* wp_lo, int64_t ldw,
-                                            const float* bias_packed, int32_t hidden_features, const float* x, int64_t ldx,
-                                            const int32_t* t_cols, int32_t d_t, float* y, int64_t ldy, float* lad_accum,
-                                            int64_t n_rows, int32_t* flags, void* stream) {
-    NFK_REQUIRE(a_lo, "NULL pointer");
-    return fused_entry(desc, inverse, a_hi, a_lo, 0, lda, wp_hi, wp_lo, ldw, bias_packed, hidden_features, x, ldx, t_cols, d_t, y,
-                       ldy, lad_accum, n_rows, flags, stream);
-}
-
-extern "C" int nfk_rq_coupling_final_tf32x3_a32(const NfkSplineDesc* desc, int inverse, const float* a, int64_t lda,
-                                                int relu_in, const float* wp_hi, const float* wp_lo, int64_t ldw,
-                                                const float* bias_packed, int32_t hidden_features, const float* x,
-                                                int64_t ldx, const int32_t* t_cols, int32_t d_t, float* y, int64_t ldy,
-                                                float* lad_accum, int64_t n_rows, int32_t* flags, void* stream) {
-    return fused_entry(desc, inverse, a, nullptr, relu_in, lda, wp_hi, wp_lo, ldw, bias_packed, hidden_features, x, ldx, t_cols,
-                       d_t, y, ldy, lad_accum, n_rows, flags, stream);
 }

@@ -2,6 +2,7 @@
 // CUTLASS headers in this image are only consulted for descriptor bit layouts, nothing is included from them).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "nfk_common.cuh"
 
@@ -10,15 +11,15 @@ namespace tc {
 
 constexpr int BM = 128;            // rows per tile = TMEM lanes
 constexpr int BN_MAX = 256;        // columns per tile (runtime BN <= BN_MAX, multiple of 16)
-constexpr int BK = 16;             // fp32 elements per K-slab = one 64-byte swizzle row (SWIZZLE_64B)
+constexpr int BK = 32;             // fp16 elements per K-slab = one 64-byte swizzle row (SWIZZLE_64B) = two UMMA K-steps
 constexpr int STAGES = 4;          // 4 x 48 KB slabs: 3 TMA loads in flight while one slab is consumed
 constexpr int THREADS = 384;        // warpgroup 0: TMA + MMA warps (2 idle); warpgroups 1-2: accumulate/epilogue
 // K-slabs accumulated inside the tensor core before the partial sum is drained to registers (precision vs drain cost):
-constexpr int DRAIN_SLABS_LINEAR = 2;   // dense layers: K = 32 (12 MMAs) -- their outputs feed log p directly
-constexpr int DRAIN_SLABS_FUSED = 4;    // fused coupling: K = 64 (24 MMAs) -- its outputs are spline logits
+constexpr int DRAIN_SLABS_LINEAR = 2;   // dense layers: K = 64 (12 MMAs) -- their outputs feed log p directly
+constexpr int DRAIN_SLABS_FUSED = 4;    // fused coupling: K = 128 (24 MMAs) -- its outputs are spline logits
 constexpr int HALF = BN_MAX / 2;     // columns per epilogue warp
-constexpr int A_BYTES = BM * BK * 4;             // 8 KB
-constexpr int B_BYTES = BN_MAX * BK * 4;         // 16 KB
+constexpr int A_BYTES = BM * BK * 2;             // 8 KB
+constexpr int B_BYTES = BN_MAX * BK * 2;         // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 KB
 // CTA-pair kernels hold half of every B tile per CTA: 32 KB stages, six of them in the same 192 KB
 constexpr int PAIR_STAGE_BYTES = 2 * A_BYTES + B_BYTES;
@@ -113,12 +114,12 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -140,12 +141,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -182,26 +183,30 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows x row bytes)
 // | [46,48) version=1 (sm_100) | [61,64) layout: 2 = SWIZZLE_128B (128-byte rows), 4 = SWIZZLE_64B (64-byte rows)
-constexpr int ROW_BYTES = BK * 4;
+constexpr int ROW_BYTES = BK * 2;
 static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "K-slab rows must be 64 or 128 bytes");
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * ROW_BYTES) >> 4) << 32) | (1ull << 46) |
            ((uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61);
 }
-// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=F16 (format 0 at [7,10) and [10,13)), K-major both, N>>3 at [17,23),
+// M>>4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int bn, int m = BM) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 
-__device__ __forceinline__ float tf32_hi(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
+// Split of one fp32 value into the fp16 pair the kernels multiply with: v * scale = hi + lo (+ <= 2^-22 relative), hi the
+// nearest fp16, lo the nearest fp16 of the exact remainder.  |v * scale| beyond the fp16 range raises NFK_FLAG_F16_RANGE.
+__device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __half& lo, int& flag) {
+    const float s = v * scale;
+    if (!(fabsf(s) <= 65000.0f)) flag |= 4;
+    hi = __float2half_rn(s);
+    lo = __float2half_rn(s - __half2float(hi));
 }
 
 // host helpers (nfk_linear_tc.cu)
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int K, int64_t ld, int box_rows);
+int make_map(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t ld, int box_rows);
 int sm_count();
 
 }  // namespace tc

@@ -143,6 +143,10 @@ def std_normal_log_prob(z, log_z, lad=None):
     return out
 
 
+class Float16RangeError(RuntimeError):
+    """A value left the representable range of the fp16 split pairs (NFK_FLAG_F16_RANGE)."""
+
+
 def raise_for_flags(flags):
     """Mirror the reference's exceptions (rational_quadratic.py:81-82, :142).  One device->host read."""
     from .transforms.base import InputOutsideDomain
@@ -151,62 +155,89 @@ def raise_for_flags(flags):
         raise InputOutsideDomain()
     if v & 2:
         raise AssertionError("rational-quadratic spline inverse: negative discriminant")
+    if v & 4:
+        raise Float16RangeError("an activation exceeded the fp16 split range of the tensor-core dense layers "
+                                "(|value| * 2^config.activation_exp > 65000): lower nflows_b200.config.activation_exp or set "
+                                "NFLOWS_B200_GEMM=simt")
 
 
-# ---- split-TF32 tensor-core dense layers ------------------------------------------------------------------------------
-def split_tf32(x, cols_i32=None, relu=False, copy_to=None):
-    """(hi, lo) operand pair of pre(x[:, cols]) for `linear_tf32x3`; optionally copies x[:, cols] into copy_to[:, cols]."""
+# ---- split-fp16 tensor-core dense layers ------------------------------------------------------------------------------
+class Pair16:
+    """fp16 split pair of an fp32 matrix: value * 2^exp = hi + lo (include/nfk.h, nfk_linear_f16x3)."""
+    __slots__ = ("hi", "lo", "exp")
+
+    def __init__(self, hi, lo, exp):
+        self.hi, self.lo, self.exp = hi, lo, int(exp)
+
+    @classmethod
+    def empty(cls, rows, cols, exp, device):
+        return cls(torch.empty(rows, cols, dtype=torch.float16, device=device),
+                   torch.empty(rows, cols, dtype=torch.float16, device=device), exp)
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def rows(self, r0, r1):
+        return Pair16(self.hi[r0:r1], self.lo[r0:r1], self.exp)
+
+    def cols(self, c0, c1):
+        return Pair16(self.hi[:, c0:c1], self.lo[:, c0:c1], self.exp)
+
+    def float(self):
+        """The represented fp32 values (tests)."""
+        return (self.hi.double() + self.lo.double()).mul_(2.0 ** -self.exp).float()
+
+
+def weight_exp(w):
+    """Power-of-two exponent that lifts max |w| to 2^14: the whole matrix, including the lo parts, stays clear of fp16's
+    subnormals and of its overflow."""
+    import math
+    amax = float(w.detach().abs().max()) if w.numel() else 0.0
+    if not (amax > 0.0) or not math.isfinite(amax):
+        return 0
+    return max(-40, min(40, 14 - math.ceil(math.log2(amax))))
+
+
+def split_f16(x, exp, relu=False, out=None, flags=None):
+    """Pair16 of pre(x) (x: 2-D fp32, unit column stride; may be a strided column block)."""
     _rows2d(x, "x")
-    n = x.shape[0]
-    c = x.shape[1] if cols_i32 is None else cols_i32.numel()
-    hi = torch.empty(n, c, dtype=torch.float32, device=x.device)
-    lo = torch.empty_like(hi)
-    if TIMELINE is not None:
-        with timed("split_%d" % c, n):
-            N.check(N.lib().nfk_split_tf32(x.data_ptr(), x.stride(0), N.ptr(cols_i32), c, int(relu), hi.data_ptr(), lo.data_ptr(),
-                                           hi.stride(0), N.ptr(copy_to), copy_to.stride(0) if copy_to is not None else 0, n,
-                                           N.stream()))
-        return hi, lo
-    N.check(N.lib().nfk_split_tf32(x.data_ptr(), x.stride(0), N.ptr(cols_i32), c, int(relu), hi.data_ptr(), lo.data_ptr(),
-                                   hi.stride(0), N.ptr(copy_to), copy_to.stride(0) if copy_to is not None else 0, n,
-                                   N.stream()))
-    return hi, lo
+    n, c = x.shape
+    pair = out if out is not None else Pair16.empty(n, c, exp, x.device)
+    if pair.exp != exp:
+        raise ValueError("destination pair has exponent {}, asked for {}".format(pair.exp, exp))
+    with timed("split_%d" % c, n):
+        N.check(N.lib().nfk_split_f16(x.data_ptr(), x.stride(0), c, int(relu), int(exp), pair.hi.data_ptr(), pair.lo.data_ptr(),
+                                      pair.hi.stride(0), n, N.ptr(flags), N.stream()))
+    return pair
 
 
-def tf32x3_supported(lda, ldw, in_features):
-    return bool(N.load().nfk_linear_tf32x3_supported(int(lda), int(ldw), int(in_features)))
+def f16x3_supported(lda, ldw, in_features):
+    return bool(N.load().nfk_linear_f16x3_supported(int(lda), int(ldw), int(in_features)))
 
 
-def linear_tf32x3(a, w_pair, bias=None, residual=None, relu_in=False, relu_out=False, want_y=True, want_split=False,
-                  split_relu=False, y_out=None, pair_out=None):
-    """tcgen05 dense layer.  `a` is either the (hi, lo) split pair of the activations or the plain fp32 activation tensor,
-    which the kernel splits on chip (after relu when relu_in).  Returns (y or None, (y_hi, y_lo) or None); y_out /
-    pair_out are caller-provided destinations (row slices of larger buffers)."""
-    w_hi, w_lo = w_pair
-    raw = not isinstance(a, tuple)
-    a_hi = _rows2d(a, "a") if raw else a[0]
-    if not raw and relu_in:
-        raise ValueError("relu_in needs the fp32 activation, not a split pair")
-    n, k = a_hi.shape
-    o = w_hi.shape[0]
-    dev = a_hi.device
+def linear_f16x3(a, w, bias=None, residual=None, relu_out=False, want_y=True, want_split=False, split_relu=False,
+                 split_exp=None, split_cols=0, y_out=None, pair_out=None, flags=None):
+    """tcgen05 dense layer on Pair16 operands.  Returns (y or None, Pair16 or None); y_out / pair_out are caller-provided
+    destinations (row slices of larger buffers).  The pair output covers the first split_cols columns (0 = all)."""
+    n, k = a.shape
+    o = w.shape[0]
+    dev = a.hi.device
     y = (y_out if y_out is not None else torch.empty(n, o, dtype=torch.float32, device=dev)) if want_y else None
+    pair = None
     if want_split:
-        pair = pair_out if pair_out is not None else (torch.empty(n, o, dtype=torch.float32, device=dev),
-                                                      torch.empty(n, o, dtype=torch.float32, device=dev))
-    else:
-        pair = None
+        from . import config
+        exp = config.activation_exp if split_exp is None else split_exp
+        pair = pair_out if pair_out is not None else Pair16.empty(n, o, exp, dev)
     if bias is not None and not bias.is_contiguous():
         bias = bias.contiguous()
-    tail = (w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), N.ptr(bias),
-            N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y), y.stride(0) if y is not None else 0,
-            N.ptr(pair[0]) if pair else 0, N.ptr(pair[1]) if pair else 0, pair[0].stride(0) if pair else 0, int(relu_out),
-            int(split_relu), n, k, o, N.stream())
     with timed("linear_%dx%d" % (k, o), n):
-        if raw:
-            N.check(N.lib().nfk_linear_tf32x3_a32(a_hi.data_ptr(), a_hi.stride(0), int(relu_in), *tail))
-        else:
-            N.check(N.lib().nfk_linear_tf32x3(a_hi.data_ptr(), a[1].data_ptr(), a_hi.stride(0), *tail))
+        N.check(N.lib().nfk_linear_f16x3(
+            a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, w.hi.data_ptr(), w.lo.data_ptr(), w.hi.stride(0), w.exp,
+            N.ptr(bias), N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y),
+            y.stride(0) if y is not None else 0, pair.hi.data_ptr() if pair else 0, pair.lo.data_ptr() if pair else 0,
+            pair.hi.stride(0) if pair else 0, pair.exp if pair else 0, int(split_cols), int(relu_out), int(split_relu), n, k, o,
+            N.ptr(flags), N.stream()))
     return y, pair
 
 
@@ -218,20 +249,10 @@ def rq_coupling_final_padded_params(num_bins, tails):
     return int(N.load().nfk_rq_coupling_final_padded_params(int(num_bins), 1 if tails == "linear" else 0))
 
 
-def rq_coupling_final(desc, inverse, a, wp_pair, bias_packed, x, t_cols, y, lad_accum, flags, relu_in=False):
-    """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel).  `a`: the (hi, lo) pair of the
-    hidden activation, or the fp32 activation itself (split on chip, after relu when relu_in).  y may be x."""
-    tail = (wp_pair[0].data_ptr(), wp_pair[1].data_ptr(), wp_pair[0].stride(0), bias_packed.data_ptr())
-    rest = (x.data_ptr(), x.stride(0), t_cols.data_ptr(), t_cols.numel(), y.data_ptr(), y.stride(0), N.ptr(lad_accum),
-            x.shape[0], N.ptr(flags), N.stream())
-    if isinstance(a, tuple):
-        if relu_in:
-            raise ValueError("relu_in needs the fp32 activation, not a split pair")
-        a_hi, a_lo = a
-        N.check(N.lib().nfk_rq_coupling_final_tf32x3(ctypes.byref(desc), int(inverse), a_hi.data_ptr(), a_lo.data_ptr(),
-                                                     a_hi.stride(0), *tail, a_hi.shape[1], *rest))
-    else:
-        _rows2d(a, "a")
-        N.check(N.lib().nfk_rq_coupling_final_tf32x3_a32(ctypes.byref(desc), int(inverse), a.data_ptr(), a.stride(0),
-                                                         int(relu_in), *tail, a.shape[1], *rest))
+def rq_coupling_final(desc, inverse, a, wp, bias_packed, x, t_cols, y, lad_accum, flags):
+    """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel).  a, wp: Pair16; y may be x."""
+    N.check(N.lib().nfk_rq_coupling_final_f16x3(
+        ctypes.byref(desc), int(inverse), a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, wp.hi.data_ptr(),
+        wp.lo.data_ptr(), wp.hi.stride(0), wp.exp, bias_packed.data_ptr(), a.shape[1], x.data_ptr(), x.stride(0),
+        t_cols.data_ptr(), t_cols.numel(), y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
     return y

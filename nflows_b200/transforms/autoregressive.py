@@ -162,15 +162,14 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
         hidden = weight.shape[1]
         fused = (use_tc and config.fuse_coupling and bias is not None
                  and K.rq_coupling_final_supported(self.num_bins, self.tails, hidden, hidden))
-        state = D.run_trunk(chain, conditioner_input, None, use_tc, want_pair=fused and config.fused_pair_input)
+        state = D.run_trunk(chain, conditioner_input, None, use_tc, flags=flags)
         if fused:
             m = self._output_dim_multiplier()
             mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
             wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.features, m, mp)
-            K.rq_coupling_final(desc, inverse, state.pair if state.pair is not None else state.raw, wp_pair, bias_packed,
-                                spline_input, all_cols, outputs, lad, flags, relu_in=chain[-1][2] and state.pair is None)
+            K.rq_coupling_final(desc, inverse, state.pair, wp_pair, bias_packed, spline_input, all_cols, outputs, lad, flags)
         else:
-            params = D.run_last(chain, state, 0, spline_input.shape[0], use_tc)
+            params = D.run_last(chain, state, 0, spline_input.shape[0], use_tc, flags=flags)
             K.rqs_rows(desc, inverse, spline_input, params, all_cols, no_cols, lad, flags, out=outputs)
         return outputs
 

@@ -110,6 +110,7 @@ class CompositeTransform(Transform):
         x = inputs
         layout = None            # None = logical column order
         owned = False            # x is a temporary of this chain (may be overwritten in place)
+        carry = {"pair": None}   # fp16 split pair of x (kernels.Pair16) when the producing kernel wrote one
         i = 0
 
         def wanted(k):
@@ -129,24 +130,27 @@ class CompositeTransform(Transform):
             if has_lu and j - i >= 1:
                 run = AffineRun.cached(self._affine_cache, leaves[i:j], x.device)
                 out_layout = wanted(j)
-                x = run.apply(x, lad, layout, out_layout)
+                pair_cols = leaves[j][0].num_identity_features if out_layout is not None else 0
+                x, pair = run.apply(x, lad, layout, out_layout, x_pair=carry["pair"], pair_cols=pair_cols, flags=flags)
+                carry["pair"] = pair
                 layout, owned = out_layout, True
                 i = j
                 continue
             want = wanted(i) if leaf._native_ready(x, context) else None
             if layout is not None and layout is not want:
                 x = K.gather_cols(x, layout.cols(x.device, inverse=True))       # back to the logical order
-                layout, owned = None, True
+                layout, owned, carry["pair"] = None, True, None
             if want is not None and layout is None:
                 x = K.gather_cols(x, want.cols(x.device))
-                layout, owned = want, True
+                layout, owned, carry["pair"] = want, True, None
             if layout is not None:
-                x = leaf._native_apply(x, lad, flags, inv, context, layout=layout, owned=owned)
+                x = leaf._native_apply(x, lad, flags, inv, context, layout=layout, owned=owned, carry=carry)
                 owned = True
             elif leaf._native_ready(x, context):
                 x = leaf._native_apply(x, lad, flags, inv, context)
-                owned = True
+                owned, carry["pair"] = True, None
             else:
+                carry["pair"] = None
                 x, l = leaf.inverse(x, context) if inv else leaf(x, context)
                 lad += l
                 if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):

@@ -116,8 +116,8 @@ class CouplingTransform(Transform):
         chain = net.dense_chain(context) if hasattr(net, "dense_chain") else None
         if chain is None or not D.chain_uses_tc(chain, self.num_identity_features) or not self._fused_final_ready(chain):
             return None
-        if (self.num_identity_features % 4) or (self.features % 4):
-            return None                                   # the strided identity view must be TMA-addressable
+        if (self.num_identity_features % 8) or (self.features % 8):
+            return None                                   # the strided fp16 identity view must be TMA-addressable
         idf, tf = self.identity_features, self.transform_features
         key = (idf.data_ptr(), idf._version, tf.data_ptr(), tf._version)
         if self._layout_cache is None or self._layout_cache[0] != key:
@@ -125,9 +125,10 @@ class CouplingTransform(Transform):
             self._layout_cache = (key, Layout(torch.cat([idf, tf]).cpu().numpy()))
         return self._layout_cache[1]
 
-    def _native_packed(self, x, lad, flags, inverse, context, owned):
-        """Fused path on a tensor already in the [identity | transformed] column order: the conditioner trunk reads the
-        identity block as a strided view, the fused kernel overwrites the transformed block in place; nothing is copied."""
+    def _native_packed(self, x, lad, flags, inverse, context, owned, carry=None):
+        """Fused path on a tensor already in the [identity | transformed] column order: the conditioner trunk reads the fp16
+        pair of the identity block (written by the affine run in front, else split here), the fused kernel overwrites the
+        transformed block in place, and the pair of that block is completed for the affine run behind; nothing is copied."""
         if not owned:
             x = x.clone()
         d_id = self.num_identity_features
@@ -135,19 +136,26 @@ class CouplingTransform(Transform):
             self._packed_cols = torch.arange(d_id, self.features, dtype=torch.int32, device=x.device)
         chain = self.transform_net.dense_chain(context)
         n = x.shape[0]
+        pair = carry["pair"] if carry is not None else None
+        if pair is None:
+            pair = K.Pair16.empty(n, self.features, D.act_exp(), x.device)
+            K.split_f16(x[:, :d_id], pair.exp, out=pair.cols(0, d_id), flags=flags)
         block = 1 << 18
         for r0 in range(0, n, block):
             r1 = min(n, r0 + block)
             xs = x[r0:r1]
-            state = D.run_trunk(chain, xs, None, True, want_pair=config.fused_pair_input, x_id=xs[:, :d_id])
+            state = D.run_trunk(chain, xs, None, True, x_pair=pair.cols(0, d_id).rows(r0, r1), flags=flags)
             with K.timed("rq_coupling_final", r1 - r0):
                 self._fused_final(chain, state, xs, self._packed_cols, xs, lad[r0:r1], flags, inverse)
+        if carry is not None:
+            K.split_f16(x[:, d_id:], pair.exp, out=pair.cols(d_id, self.features), flags=flags)
+            carry["pair"] = pair
         return x
 
-    def _native_apply(self, inputs, lad, flags, inverse, context=None, layout=None, owned=False):
+    def _native_apply(self, inputs, lad, flags, inverse, context=None, layout=None, owned=False, carry=None):
         self._check_inputs(inputs)
         if layout is not None:
-            return self._native_packed(inputs, lad, flags, inverse, context, owned)
+            return self._native_packed(inputs, lad, flags, inverse, context, owned, carry)
         if self.unconditional_transform is None:
             return self._native_coupling(inputs, lad, flags, inverse, context)
         # identity half additionally goes through its own elementwise transform (coupling.py:90-94 forward: after the
@@ -191,7 +199,7 @@ class CouplingTransform(Transform):
             block = 1 << 18
             for r0 in range(0, n, block):
                 r1 = min(n, r0 + block)
-                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, want_pair=config.fused_pair_input)
+                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, flags=flags)
                 with K.timed("rq_coupling_final", r1 - r0):
                     self._fused_final(chain, state, outputs[r0:r1], t_cols, outputs[r0:r1], lad[r0:r1], flags, inverse)
             return outputs
@@ -210,11 +218,11 @@ class CouplingTransform(Transform):
                 self._native_epilogue(xs, params.float().contiguous(), t_cols, id_cols, outputs[r0:r1], lad[r0:r1], flags,
                                       inverse)
                 continue
-            state = D.run_trunk(chain, xs, id_cols, use_tc)
+            state = D.run_trunk(chain, xs, id_cols, use_tc, flags=flags)
             for q0 in range(0, r1 - r0, final_rows):
                 q1 = min(r1 - r0, q0 + final_rows)
                 with K.timed("final_linear", q1 - q0):
-                    params = D.run_last(chain, state, q0, q1, use_tc)
+                    params = D.run_last(chain, state, q0, q1, use_tc, flags=flags)
                 with K.timed("spline_epilogue", q1 - q0):
                     self._native_epilogue(xs[q0:q1], params, t_cols, id_cols, outputs[r0 + q0:r0 + q1],
                                           lad[r0 + q0:r0 + q1], flags, inverse)
@@ -401,5 +409,4 @@ class PiecewiseRationalQuadraticCouplingTransform(PiecewiseCouplingTransform):
         m = self._transform_dim_multiplier()
         mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
         wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.num_transform_features, m, mp)
-        K.rq_coupling_final(self._spline_desc(), inverse, state.pair if state.pair is not None else state.raw, wp_pair,
-                            bias_packed, x, t_cols, out, lad, flags, relu_in=chain[-1][2] and state.pair is None)
+        K.rq_coupling_final(self._spline_desc(), inverse, state.pair, wp_pair, bias_packed, x, t_cols, out, lad, flags)

@@ -130,9 +130,10 @@ class AffineRun:
             cache[key] = hit
         return hit[1]
 
-    def apply(self, x, lad, in_layout=None, out_layout=None):
+    def apply(self, x, lad, in_layout=None, out_layout=None, x_pair=None, pair_cols=0, flags=None):
+        """Returns (y, Pair16 of y's first pair_cols columns or None)."""
         weight, bias = self.operands(in_layout, out_layout)
-        y = D.affine_map(x, weight, bias)
+        y, y_pair = D.affine_map(x, weight, bias, x_pair=x_pair, pair_cols=pair_cols, flags=flags)
         if self.lad_const != 0.0:
             K.add_const_(lad, self.lad_const)
-        return y
+        return y, y_pair

@@ -71,7 +71,7 @@ class LULinear(Linear):
         from .fused_affine import AffineRun
         if inputs.shape[1] != self.features:
             raise ValueError("Expected features = {}, got {}.".format(self.features, inputs.shape[1]))
-        return AffineRun.cached(self._native_cache, [(self, inverse)], inputs.device).apply(inputs, lad)
+        return AffineRun.cached(self._native_cache, [(self, inverse)], inputs.device).apply(inputs, lad, flags=flags)[0]
 
     # ---- torch path ---------------------------------------------------------------------------------------
     def forward_no_cache(self, inputs):

@@ -1,5 +1,5 @@
-"""One trunk-shaped tensor-core dense layer (n=2^18, fp32 activation split on chip, relu in, residual, fp32 out) -- ncu
-target and quick timing.  usage: linear_only.py [K] [N] [mode]   mode: a32 (default) | pair"""
+"""One trunk-shaped tensor-core dense layer (n=2^18, fp16 split-pair operands, residual, fp32 out) -- ncu
+target and quick timing.  usage: linear_only.py [K] [N] [mode]   mode: y (fp32 output only, default) | pair (fp32 + fp16 pair output)"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,16 +8,14 @@ dev = torch.device("cuda:0")
 n = 1 << 18
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 o = int(sys.argv[2]) if len(sys.argv) > 2 else 256
-mode = sys.argv[3] if len(sys.argv) > 3 else "a32"
+mode = sys.argv[3] if len(sys.argv) > 3 else "y"
 x = torch.randn(n, k, device=dev); w = torch.randn(o, k, device=dev) / k ** 0.5; b = torch.randn(o, device=dev)
 r = torch.randn(n, o, device=dev)
-wp = K.split_tf32(w)
+wp = K.split_f16(w, K.weight_exp(w))
 y = torch.empty(n, o, device=dev)
-if mode == "pair":
-    xp = K.split_tf32(x, relu=True)
-    run = lambda: K.linear_tf32x3(xp, wp, b, residual=r, want_y=True, y_out=y)
-else:
-    run = lambda: K.linear_tf32x3(x, wp, b, residual=r, relu_in=True, want_y=True, y_out=y)
+xp = K.split_f16(x, 6, relu=True)
+pair = K.Pair16.empty(n, o, 6, dev)
+run = lambda: K.linear_f16x3(xp, wp, b, residual=r, want_y=True, y_out=y, want_split=mode == "pair", pair_out=pair if mode == "pair" else None)
 for _ in range(3):
     run()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
