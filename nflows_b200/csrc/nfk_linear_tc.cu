@@ -28,7 +28,12 @@
 //                                tcgen05.ld of each partial sum -> 128 running sums per thread in registers; at the end of
 //                                a tile scale / relu / residual -> global stores of the fp32 result and/or the fp16 pair
 //                                consumed by the next layer
-//   smem ring: 4 stages x (A_hi, A_lo, W_hi, W_lo) of K = 32 = 4 x 48 KB;  TMEM: 2 partial accumulators x 256 columns.
+//                                consumed by the next layer.  Outputs leave through shared memory: each warp stages 32-row x
+//                                128-byte chunks (SWIZZLE_128B, conflict-free) and one lane issues a TMA store per chunk --
+//                                full-line writes instead of the 32-sector scatter of a row-per-thread st.global (ncu, r1:
+//                                the epilogue warps spent 43 % of their samples waiting for the LSU to drain those stores)
+//   smem: 3 stages x (A_hi, A_lo, W_hi, W_lo) of K = 32 = 3 x 48 KB, + 8 warps x 2 x 4 KB store staging;
+//   TMEM: 2 partial accumulators x 256 columns.
 #include <stdlib.h>
 
 #include <mutex>
@@ -56,7 +61,20 @@ struct Params {
     int split_relu;          // relu applied before splitting (the next layer consumes relu(y))
     int num_m_tiles, num_n_tiles;
     int n_inner;             // tile schedule, see tile_of()
+    int tma_store;           // outputs are TMA-addressable (16-byte aligned bases and row pitches): staged stores
 };
+
+constexpr int LIN_STAGES = 3;
+constexpr int LIN_STG_OFF = LIN_STAGES * STAGE_BYTES + 1024;            // after the ring and the barrier block, 1024-aligned
+constexpr int LIN_STG_BYTES = 4096;                                     // one 32-row x 128-byte chunk
+constexpr int LIN_SMEM_BYTES = LIN_STG_OFF + 8 * 2 * LIN_STG_BYTES + 1024 /*alignment slack*/;
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 
 // Tile schedule of a persistent CTA.  With at least one 128-row block per CTA ("n_inner") a CTA walks all column tiles of
 // its row block back to back, so the A slabs it just streamed are re-read from L2, not from HBM (K = N = 784: 4 column
@@ -84,7 +102,9 @@ template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                     const Params p) {
+                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yh,
+                     const __grid_constant__ CUtensorMap map_yl, const Params p) {
+    constexpr int STAGES = LIN_STAGES;                                     // (shadows the 4-stage ring of the fused kernel)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -211,6 +231,9 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         int flag = 0;
         const bool vec_r = p.residual && (p.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
         const bool vec_b = !p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+        uint8_t* stg_gen = smem_gen + LIN_STG_OFF + (warp - 4) * 2 * LIN_STG_BYTES;      // this warp's two store-staging chunks
+        const uint32_t stg_u32 = smem_base + LIN_STG_OFF + (warp - 4) * 2 * LIN_STG_BYTES;
+        int stg_buf = 0;
         int tm, tn;
         for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
             const int64_t row = (int64_t)tm * BM + q * 32 + lane;
@@ -286,7 +309,110 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (row < p.n_rows) {
+            if (p.tma_store) {
+                // ---- finish the values in place ...
+                const bool row_ok = row < p.n_rows;
+#pragma unroll
+                for (int c = 0; c < HALF; ++c) {
+                    float x = sum[c] * p.inv_acc_scale;
+                    if (p.relu_out) x = fmaxf(x, 0.0f);
+                    sum[c] = x;
+                }
+                if (p.residual && !fold_residual) {
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 4) {
+                        const int col = n0 + c;
+                        if (!row_ok || c + half * HALF >= p.BN || col >= p.N) continue;
+                        const float* rp = p.residual + row * p.ldr + col;
+                        if (vec_r && col + 3 < p.N) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rp);
+                            sum[c] += r4.x; sum[c + 1] += r4.y; sum[c + 2] += r4.z; sum[c + 3] += r4.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (col + j < p.N) sum[c + j] += rp[j];
+                        }
+                    }
+                }
+                // ---- ... and send them out chunk by chunk: [32 rows][128 bytes] per TMA store, 16-byte pieces XOR-swizzled
+                // by the row (SWIZZLE_128B) so the row-per-lane st.shared is conflict-free; the TMA unit clips rows/columns
+                // beyond the tensor, so ragged tiles need no guards
+                const int row0 = tm * BM + q * 32;
+                auto stage_begin = [&]() -> uint4* {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the chunk before last has left
+                    __syncwarp();
+                    return reinterpret_cast<uint4*>(stg_gen + stg_buf * LIN_STG_BYTES) + lane * 8;
+                };
+                auto stage_end = [&](const CUtensorMap* map, int c0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(map, stg_u32 + stg_buf * LIN_STG_BYTES, c0, row0);
+                    stg_buf ^= 1;
+                };
+                if (p.y) {
+#pragma unroll
+                    for (int ch = 0; ch < HALF / 32; ++ch) {
+                        const int col0 = n0 + 32 * ch;
+                        if (32 * ch + half * HALF >= p.BN || col0 >= p.N) continue;
+                        if (32 * ch + 32 + half * HALF > p.BN) {           // chunk straddles the tile's right edge: the columns
+                            if (row_ok) {                                  // beyond it belong to the next tile -> guarded stores
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (32 * ch + j + half * HALF < p.BN && col0 + j < p.N) p.y[row * p.ldy + col0 + j] = sum[32 * ch + j];
+                            }
+                            continue;
+                        }
+                        uint4* dst = stage_begin();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            dst[j ^ (lane & 7)] = make_uint4(__float_as_uint(sum[32 * ch + 4 * j]), __float_as_uint(sum[32 * ch + 4 * j + 1]),
+                                                             __float_as_uint(sum[32 * ch + 4 * j + 2]), __float_as_uint(sum[32 * ch + 4 * j + 3]));
+                        stage_end(&map_y, col0);
+                    }
+                }
+                if (p.y_hi) {
+#pragma unroll
+                    for (int ch = 0; ch < HALF / 64; ++ch) {
+                        const int col0 = n0 + 64 * ch;
+                        if (64 * ch + half * HALF >= p.BN || col0 >= p.N || col0 >= p.split_n) continue;
+                        if (64 * ch + 64 + half * HALF > p.BN) {           // straddles the tile's right edge: guarded stores
+                            if (row_ok) {
+#pragma unroll
+                                for (int j = 0; j < 64; ++j) {
+                                    if (64 * ch + j + half * HALF < p.BN && col0 + j < p.N && col0 + j < p.split_n) {
+                                        float x = sum[64 * ch + j];
+                                        if (p.split_relu) x = fmaxf(x, 0.0f);
+                                        __half hi, lo;
+                                        split_f16(x, p.out_scale, hi, lo, flag);
+                                        p.y_hi[row * p.lds + col0 + j] = hi;
+                                        p.y_lo[row * p.lds + col0 + j] = lo;
+                                    }
+                                }
+                            }
+                            continue;
+                        }
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {                     // hi chunk, then lo chunk
+                            uint4* dst = stage_begin();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                __half h8[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    float x = sum[64 * ch + 8 * j + e];
+                                    if (p.split_relu) x = fmaxf(x, 0.0f);
+                                    __half hi, lo;
+                                    int f2 = 0;
+                                    split_f16(x, p.out_scale, hi, lo, f2);
+                                    if (part == 0 && row_ok && col0 + 8 * j + e < p.N) flag |= f2;
+                                    h8[e] = part == 0 ? hi : lo;
+                                }
+                                dst[j ^ (lane & 7)] = *reinterpret_cast<const uint4*>(h8);
+                            }
+                            stage_end(part == 0 ? &map_yh : &map_yl, col0);
+                        }
+                    }
+                }
+            } else if (row < p.n_rows) {
 #pragma unroll
                 for (int c = 0; c < HALF; c += 16) {
                     const int col0 = n0 + c;
@@ -346,6 +472,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             }
             __syncwarp();
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its stores
         if (flag && p.flags) atomicOr(p.flags, flag);
     }
 
@@ -407,6 +534,22 @@ static EncodeTiledFn encode_fn() {
             fn = reinterpret_cast<EncodeTiledFn>(sym);
     });
     return fn;
+}
+
+// 2-D map of an output tensor for the staged TMA stores: boxes of 32 rows x 128 bytes, SWIZZLE_128B
+static int make_store_map(CUtensorMap* map, void* base, bool fp16, int64_t rows, int64_t cols, int64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const int es = fp16 ? 2 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)r);
+    return NFK_OK;
 }
 
 int make_map(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t ld, int box_rows) {
@@ -503,13 +646,22 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     if ((rc = tc::make_map(&ma_lo, a_lo, n_rows, in_features, lda, tc::BM))) return rc;
     if ((rc = tc::make_map(&mw_hi, w_hi, out_features, in_features, ldw, bn / CL))) return rc;
     if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn / CL))) return rc;
+    // staged TMA stores need 16-byte aligned bases and row pitches for every requested output
+    CUtensorMap my = mw_hi, myh = mw_hi, myl = mw_hi;      // placeholders when an output is absent (never dereferenced)
+    p.tma_store = (!Y || (aligned16(Y) && ldy % 4 == 0)) && (!y_hi || (aligned16(y_hi) && aligned16(y_lo) && lds % 8 == 0)) ? 1 : 0;
+    if (p.tma_store) {
+        const int64_t pn = p.split_n < out_features ? p.split_n : out_features;
+        if (Y && (rc = tc::make_store_map(&my, Y, false, n_rows, out_features, ldy))) return rc;
+        if (y_hi && (rc = tc::make_store_map(&myh, y_hi, true, n_rows, pn, lds))) return rc;
+        if (y_hi && (rc = tc::make_store_map(&myl, y_lo, true, n_rows, pn, lds))) return rc;
+    }
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::SMEM_BYTES, cudaGetErrorString(e));
+            e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::LIN_SMEM_BYTES, cudaGetErrorString(e));
         attr_set = true;
     }
     const int units = (p.num_m_tiles + CL - 1) / CL;
@@ -519,15 +671,15 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(CL * (work < max_clusters ? work : max_clusters)));
     cfg.blockDim = dim3(tc::THREADS);
-    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.dynamicSmemBytes = tc::LIN_SMEM_BYTES;
     cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, p)
-                               : cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, p)
+                               : cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, p);
     if (le != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(linear_f16x3_kernel, cluster %d): %s", CL, cudaGetErrorString(le));
     return check_launch("linear_f16x3_kernel");
 }

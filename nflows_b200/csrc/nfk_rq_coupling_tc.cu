@@ -23,7 +23,8 @@ struct FusedParams {
     const float* bias;      // [d_t * MP] packed like the weight rows, zero padded
     const float* x;         // coupling input [n_rows, ldx]
     float* y;               // coupling output [n_rows, ldy]; identity columns are written by the caller
-    const int32_t* t_cols;  // [d_t] column of transformed feature j
+    const int32_t* t_cols;  // [d_t] column of transformed feature j, or null: feature j lives in column t_col0 + j
+    int t_col0;
     float* lad_accum;       // [n_rows] running log|det| (read-modify-write) or null
     int32_t* flags;
     int64_t ldx, ldy, n_rows;
@@ -209,14 +210,22 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
     const uint32_t bar_full = bars, bar_empty = bars + 8 * NST;
     const uint32_t bar_tfull = bars + 16 * NST, bar_tempty = bars + 16 * NST + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * NST + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * NST + 32);   // then bias barriers at +48, +64
     float* s_lad = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256);       // [EWG-1][128] partial log|det|
+    // the packed bias of the current / next column tile, staged by the producer with a bulk copy so the epilogue reads it
+    // with ~30-cycle shared loads (ncu, r1: bias + x + column-index loads at the top of every tile, L2 latency each, were
+    // 40 % of the epilogue warps' samples)
+    float* s_bias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256 + 512 * EWG);   // [2][BN_MAX]
+    const uint32_t bar_bfull = bars + 16 * NST + 48, bar_bempty = bars + 16 * NST + 64;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t tid_x;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));      // volatile: not re-read (S2R) inside the tile loop
+    const int warp = tid_x >> 5, lane = tid_x & 31;
     const int num_k = (p.K + BK - 1) / BK;
     const int num_groups = (num_k + DRAIN_SLABS_FUSED - 1) / DRAIN_SLABS_FUSED;     // partial sums per tile
 
-    if (threadIdx.x == 0) {
+    if (tid_x == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_bfull + 8 * b, 1); mbar_init(bar_bempty + 8 * b, 4 * EWG); }
         // MODE 2: both CTAs' MMA threads release a slot (the peer multicasts into it); MODE 3: the leader's commit reaches
         // both CTAs' barriers, and the leader's accumulator barrier collects the epilogue warps of BOTH CTAs
         for (int s = 0; s < NST; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, MODE == 2 ? 2 : 1); }
@@ -245,9 +254,18 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                                                    : 2u * A_BYTES + 2u * (uint32_t)BN * ROW_BYTES;
                 constexpr int WROWS = BN / CL;                                             // weight rows this CTA fetches
                 int stage = 0; uint32_t phase = 0;
+                int bslot = 0; uint32_t bphase = 0;
                 for (int mb = first_block; mb < num_blocks; mb += block_step) {
                     const int m = mb * CL + cta_rank;
                     for (int n = 0; n < p.num_n_tiles; ++n) {
+                        {   // this tile's slice of the packed bias -> s_bias[bslot]
+                            const int cols = min(TILE, p.d_t * MP - n * TILE);
+                            mbar_wait(bar_bempty + 8 * bslot, bphase ^ 1);
+                            mbar_expect_tx(bar_bfull + 8 * bslot, (uint32_t)cols * 4u);
+                            bulk_load_1d(smem_u32(s_bias + bslot * BN_MAX), p.bias + (int64_t)n * TILE, (uint32_t)cols * 4u,
+                                         bar_bfull + 8 * bslot);
+                            if (++bslot == 2) { bslot = 0; bphase ^= 1; }
+                        }
                         for (int ks = 0; ks < num_k; ++ks) {
                             mbar_wait(bar_empty + 8 * stage, phase ^ 1);      // every CTA of the cluster has released the slot
                             const uint32_t full = bar_full + 8 * stage;
@@ -352,37 +370,36 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         const int half = (warp - 4) >> 2;         // warpgroup: which FPT features of the tile
         int acc = 0; uint32_t acc_phase = 0;
         int flag = 0;
+        int bslot = 0; uint32_t bphase = 0;
         for (int mb = first_block; mb < num_blocks; mb += block_step) {
             const int m = mb * CL + cta_rank;
             const int64_t row = (int64_t)m * BM + q * 32 + lane;
             const bool row_ok = row < p.n_rows;
             float lad_row = 0.0f;
-            for (int n = 0; n < p.num_n_tiles; ++n) {
-                const int j0 = (n * EWG + half) * FPT;                     // first feature this thread owns in this tile
-                float xin[FPT];
-                int col[FPT];
+            // input values and columns of the FPT features this thread owns in a tile; loaded one tile ahead so their latency
+            // hides under the spline of the tile before (y may alias x: the columns of different tiles are disjoint and every
+            // element is read, then written, by this thread only)
+            float xin[FPT], xin_next[FPT];
+            int col[FPT], col_next[FPT];
+            auto load_x = [&](int n, float (&xv)[FPT], int (&cv)[FPT]) {
+                const int jn = (n * EWG + half) * FPT;
 #pragma unroll
                 for (int f = 0; f < FPT; ++f) {
-                    const bool ok = row_ok && (j0 + f < p.d_t);
-                    col[f] = ok ? __ldg(p.t_cols + j0 + f) : 0;
-                    xin[f] = ok ? p.x[row * p.ldx + col[f]] : 0.0f;       // plain load: y may alias x (each element is read, then written, by this thread only)
+                    const bool ok = row_ok && (jn + f < p.d_t);
+                    cv[f] = !ok ? 0 : (p.t_cols ? __ldg(p.t_cols + jn + f) : p.t_col0 + jn + f);
+                    xv[f] = ok ? p.x[row * p.ldx + cv[f]] : 0.0f;
                 }
-                // running sums start from the packed bias of this thread's columns; all loads are issued back-to-back here -- a
-                // load/add pair per column inside the first drain serialised 120 L1 latencies per tile (ncu: 37 % of the
-                // epilogue warps' samples)
-                const float4* bias_tile = reinterpret_cast<const float4*>(p.bias + (int64_t)j0 * MP);
+            };
+            load_x(0, xin, col);
+            for (int n = 0; n < p.num_n_tiles; ++n) {
+                const int j0 = (n * EWG + half) * FPT;                     // first feature this thread owns in this tile
                 float sum[HC];
 #pragma unroll
-                for (int c = 0; c < HC; c += 4) {
-                    const float4 b4 = (j0 + c / MP < p.d_t) ? __ldg(bias_tile + (c >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    sum[c] = b4.x * p.acc_scale; sum[c + 1] = b4.y * p.acc_scale;      // the sums live in the accumulators'
-                    sum[c + 2] = b4.z * p.acc_scale; sum[c + 3] = b4.w * p.acc_scale;  // power-of-two scaled domain (exact)
-                }
+                for (int c = 0; c < HC; ++c) sum[c] = 0.0f;
                 for (int ks = 0; ks < num_groups; ++ks) {
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HC;
-#pragma unroll
                     constexpr int LDB = HC <= 48 ? 3 : 5;           // TMEM loads in flight per wait (register budget)
 #pragma unroll
                     for (int c = 0; c < HC; c += 8 * LDB) {
@@ -411,9 +428,22 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                // ---- spline on the FPT features held in registers, all features advanced together (ILP = FPT)
+                if (n + 1 < p.num_n_tiles) load_x(n + 1, xin_next, col_next);
+                // ---- back from the accumulators' power-of-two scaled domain, plus the packed bias staged in shared memory
+                {
+                    mbar_wait(bar_bfull + 8 * bslot, bphase);
+                    const float4* bias4 = reinterpret_cast<const float4*>(s_bias + bslot * BN_MAX + half * HC);
 #pragma unroll
-                for (int c = 0; c < HC; ++c) sum[c] *= p.inv_acc_scale;
+                    for (int c = 0; c < HC; c += 4) {
+                        const float4 b4 = (j0 + c / MP < p.d_t) ? bias4[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        sum[c] = fmaf(sum[c], p.inv_acc_scale, b4.x); sum[c + 1] = fmaf(sum[c + 1], p.inv_acc_scale, b4.y);
+                        sum[c + 2] = fmaf(sum[c + 2], p.inv_acc_scale, b4.z); sum[c + 3] = fmaf(sum[c + 3], p.inv_acc_scale, b4.w);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_bempty + 8 * bslot);
+                    if (++bslot == 2) { bslot = 0; bphase ^= 1; }
+                }
+                // ---- spline on the FPT features held in registers, all features advanced together (ILP = FPT)
                 {
                     float yy[FPT], ll[FPT];
                     rqs_eval_multi<NB, TAILS, FPT, MP>(p.sp, p.inverse != 0, xin, sum, yy, ll, flag);
@@ -425,6 +455,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                         }
                     }
                 }
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) { xin[f] = xin_next[f]; col[f] = col_next[f]; }
                 __syncwarp();
             }
             // ---- finish the row block: lad_accum[row] += the warpgroups' partial sums, fixed order
@@ -471,7 +503,7 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     if ((rc = make_map(&mw_hi, w_hi, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
     if ((rc = make_map(&mw_lo, w_lo, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
     p.num_n_tiles = (p.d_t + Cfg::TILE_FEATURES - 1) / Cfg::TILE_FEATURES;
-    constexpr int smem = SMEM_BYTES + 512 * EWG;
+    constexpr int smem = SMEM_BYTES + 512 * EWG + 2 * BN_MAX * 4;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -523,8 +555,8 @@ extern "C" int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t
 extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int inverse, const void* a_hi_, const void* a_lo_,
                                           int64_t lda, int32_t a_exp, const void* wp_hi_, const void* wp_lo_, int64_t ldw,
                                           int32_t w_exp, const float* bias_packed, int32_t hidden_features, const float* x,
-                                          int64_t ldx, const int32_t* t_cols, int32_t d_t, float* y, int64_t ldy,
-                                          float* lad_accum, int64_t n_rows, int32_t* flags, void* stream) {
+                                          int64_t ldx, const int32_t* t_cols, int32_t t_col0, int32_t d_t, float* y,
+                                          int64_t ldy, float* lad_accum, int64_t n_rows, int32_t* flags, void* stream) {
     const __half* a_hi = (const __half*)a_hi_; const __half* a_lo = (const __half*)a_lo_;
     const __half* wp_hi = (const __half*)wp_hi_; const __half* wp_lo = (const __half*)wp_lo_;
     tc::FusedParams p;
@@ -532,13 +564,15 @@ extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int invers
     if (rc) return rc;
     NFK_REQUIRE(n_rows >= 0 && d_t >= 1 && hidden_features >= 1, "bad sizes");
     if (n_rows == 0) return NFK_OK;
-    NFK_REQUIRE(a_hi && a_lo && wp_hi && wp_lo && bias_packed && x && t_cols && y, "NULL pointer");
+    NFK_REQUIRE(a_hi && a_lo && wp_hi && wp_lo && bias_packed && x && y, "NULL pointer");
+    NFK_REQUIRE(t_cols || t_col0 >= 0, "t_cols is NULL and t_col0 is negative");
+    NFK_REQUIRE(aligned16(bias_packed), "bias_packed must be 16-byte aligned");
     NFK_REQUIRE(nfk_rq_coupling_final_supported(desc->num_bins, desc->linear_tails, hidden_features, lda) && ldw % 8 == 0,
                 "fused coupling kernel does not take num_bins=%d hidden=%d", desc->num_bins, hidden_features);
     NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(wp_hi) && aligned16(wp_lo), "operands must be 16-byte aligned");
     NFK_REQUIRE(n_rows < (1ll << 31), "n_rows too large for one launch");
     NFK_REQUIRE(a_exp + w_exp >= -60 && a_exp + w_exp <= 60, "scale exponent out of range");
-    p.bias = bias_packed; p.x = x; p.y = y; p.t_cols = t_cols; p.lad_accum = lad_accum; p.flags = flags;
+    p.bias = bias_packed; p.x = x; p.y = y; p.t_cols = t_cols; p.t_col0 = t_col0; p.lad_accum = lad_accum; p.flags = flags;
     p.ldx = ldx; p.ldy = ldy; p.n_rows = n_rows; p.K = hidden_features; p.d_t = d_t; p.inverse = inverse;
     p.acc_scale = ldexpf(1.0f, a_exp + w_exp); p.inv_acc_scale = ldexpf(1.0f, -(a_exp + w_exp));
     p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);

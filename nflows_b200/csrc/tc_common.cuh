@@ -57,6 +57,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// 1-D bulk copy global -> this CTA's shared memory, bytes (multiple of 16, 16-byte aligned both sides) counted on `bar`
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 // ---- thread-block-cluster variants: one TMA box delivered to the same smem offset of every CTA in `mask`, each
 // destination CTA's mbarrier (same offset) receives the bytes; tcgen05.commit arriving on the barrier of every CTA in `mask`
 __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,

@@ -250,9 +250,14 @@ def rq_coupling_final_padded_params(num_bins, tails):
 
 
 def rq_coupling_final(desc, inverse, a, wp, bias_packed, x, t_cols, y, lad_accum, flags):
-    """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel).  a, wp: Pair16; y may be x."""
+    """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel).  a, wp: Pair16; y may be x.
+    t_cols: int32 column index tensor of the transformed features, or (first_column, count) when they are consecutive."""
+    if isinstance(t_cols, tuple):
+        cols_ptr, col0, d_t = 0, int(t_cols[0]), int(t_cols[1])
+    else:
+        cols_ptr, col0, d_t = t_cols.data_ptr(), -1, t_cols.numel()
     N.check(N.lib().nfk_rq_coupling_final_f16x3(
         ctypes.byref(desc), int(inverse), a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, wp.hi.data_ptr(),
         wp.lo.data_ptr(), wp.hi.stride(0), wp.exp, bias_packed.data_ptr(), a.shape[1], x.data_ptr(), x.stride(0),
-        t_cols.data_ptr(), t_cols.numel(), y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
+        cols_ptr, col0, d_t, y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
     return y

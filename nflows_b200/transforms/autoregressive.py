@@ -167,7 +167,8 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
             m = self._output_dim_multiplier()
             mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
             wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.features, m, mp)
-            K.rq_coupling_final(desc, inverse, state.pair, wp_pair, bias_packed, spline_input, all_cols, outputs, lad, flags)
+            K.rq_coupling_final(desc, inverse, state.pair, wp_pair, bias_packed, spline_input, (0, self.features), outputs, lad,
+                                flags)
         else:
             params = D.run_last(chain, state, 0, spline_input.shape[0], use_tc, flags=flags)
             K.rqs_rows(desc, inverse, spline_input, params, all_cols, no_cols, lad, flags, out=outputs)

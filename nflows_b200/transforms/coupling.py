@@ -132,8 +132,6 @@ class CouplingTransform(Transform):
         if not owned:
             x = x.clone()
         d_id = self.num_identity_features
-        if self._packed_cols is None or self._packed_cols.device != x.device:
-            self._packed_cols = torch.arange(d_id, self.features, dtype=torch.int32, device=x.device)
         chain = self.transform_net.dense_chain(context)
         n = x.shape[0]
         pair = carry["pair"] if carry is not None else None
@@ -146,7 +144,7 @@ class CouplingTransform(Transform):
             xs = x[r0:r1]
             state = D.run_trunk(chain, xs, None, True, x_pair=pair.cols(0, d_id).rows(r0, r1), flags=flags)
             with K.timed("rq_coupling_final", r1 - r0):
-                self._fused_final(chain, state, xs, self._packed_cols, xs, lad[r0:r1], flags, inverse)
+                self._fused_final(chain, state, xs, (d_id, self.features - d_id), xs, lad[r0:r1], flags, inverse)
         if carry is not None:
             K.split_f16(x[:, d_id:], pair.exp, out=pair.cols(d_id, self.features), flags=flags)
             carry["pair"] = pair
