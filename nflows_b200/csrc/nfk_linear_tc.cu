@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(THREADS, 1)
 linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                      const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yh,
-                     const __grid_constant__ CUtensorMap map_yl, const Params p) {
+                     const __grid_constant__ CUtensorMap map_yl, const __grid_constant__ CUtensorMap map_y_tail,
+                     const __grid_constant__ CUtensorMap map_yh_tail, const __grid_constant__ CUtensorMap map_yl_tail,
+                     const Params p) {
     constexpr int STAGES = LIN_STAGES;                                     // (shadows the 4-stage ring of the fused kernel)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
@@ -242,6 +244,19 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             // start of the tile, and complete under the first MMAs instead of stalling the tile epilogue (ncu: the serialised
             // DRAM-latency residual reads of the epilogue held up drains -> MMA -> TMA; 15 % tensor activity on 256x256).
             const bool fold_residual = p.residual && !p.relu_out;
+            if (p.residual) {      // pull the NEXT tile's residual rows towards L2 while this tile is computed
+                int nm, nn;
+                if (tile_of<CL>(it + 1, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, nm, nn)) {
+                    const int64_t nrow = (int64_t)nm * BM + q * 32 + lane;
+                    const int ncol = nn * p.BN + half * HALF;
+                    if (nrow < p.n_rows) {
+#pragma unroll
+                        for (int c = 0; c < HALF; c += 32)
+                            if (ncol + c < p.N && c + half * HALF < p.BN)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + nrow * p.ldr + ncol + c));
+                    }
+                }
+            }
             float sum[HALF];
             // pass 1: every residual load is issued before anything depends on one (in-order issue: a dependent add between
             // two loads would serialise the DRAM latencies)
@@ -353,12 +368,19 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     for (int ch = 0; ch < HALF / 32; ++ch) {
                         const int col0 = n0 + 32 * ch;
                         if (32 * ch + half * HALF >= p.BN || col0 >= p.N) continue;
-                        if (32 * ch + 32 + half * HALF > p.BN) {           // chunk straddles the tile's right edge: the columns
-                            if (row_ok) {                                  // beyond it belong to the next tile -> guarded stores
+                        if (32 * ch + 32 + half * HALF > p.BN) {           // chunk straddles the tile's right edge (the columns
+                            // beyond it belong to the next tile): a narrower, unswizzled [32][16 floats] chunk through its own map
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+                            uint4* dst = reinterpret_cast<uint4*>(stg_gen) + lane * 4;
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (32 * ch + j + half * HALF < p.BN && col0 + j < p.N) p.y[row * p.ldy + col0 + j] = sum[32 * ch + j];
-                            }
+                            for (int j = 0; j < 4; ++j)
+                                dst[j] = make_uint4(__float_as_uint(sum[32 * ch + 4 * j]), __float_as_uint(sum[32 * ch + 4 * j + 1]),
+                                                    __float_as_uint(sum[32 * ch + 4 * j + 2]), __float_as_uint(sum[32 * ch + 4 * j + 3]));
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) tma_store_2d(&map_y_tail, stg_u32, col0, row0);
+                            stg_buf = 1;
                             continue;
                         }
                         uint4* dst = stage_begin();
@@ -374,42 +396,43 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     for (int ch = 0; ch < HALF / 64; ++ch) {
                         const int col0 = n0 + 64 * ch;
                         if (64 * ch + half * HALF >= p.BN || col0 >= p.N || col0 >= p.split_n) continue;
-                        if (64 * ch + 64 + half * HALF > p.BN) {           // straddles the tile's right edge: guarded stores
-                            if (row_ok) {
+                        const int tail = p.BN - half * HALF - 64 * ch;     // < 64: chunk straddles the tile's right edge -> narrow chunk
+                        const bool is_tail = tail < 64;
+                        // both halves of the pair are formed once and staged in the warp's two chunks at the same time
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        // full chunk: [32][128 B] swizzled; tail chunk: [32][2 * tail B] plain row-major (tail = 16, 32 or 48 columns)
+                        const int pieces = is_tail ? tail >> 3 : 8;         // 16-byte pieces per row
+                        uint4* dh = reinterpret_cast<uint4*>(stg_gen) + lane * pieces;
+                        uint4* dl = reinterpret_cast<uint4*>(stg_gen + LIN_STG_BYTES) + lane * pieces;
+                        float amax = 0.0f;
 #pragma unroll
-                                for (int j = 0; j < 64; ++j) {
-                                    if (64 * ch + j + half * HALF < p.BN && col0 + j < p.N && col0 + j < p.split_n) {
-                                        float x = sum[64 * ch + j];
-                                        if (p.split_relu) x = fmaxf(x, 0.0f);
-                                        __half hi, lo;
-                                        split_f16(x, p.out_scale, hi, lo, flag);
-                                        p.y_hi[row * p.lds + col0 + j] = hi;
-                                        p.y_lo[row * p.lds + col0 + j] = lo;
-                                    }
-                                }
+                        for (int j = 0; j < 8; ++j) {
+                            __half2 h2[4], l2[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                float x0 = sum[64 * ch + 8 * j + 2 * e], x1 = sum[64 * ch + 8 * j + 2 * e + 1];
+                                if (p.split_relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+                                x0 *= p.out_scale; x1 *= p.out_scale;
+                                if (j < pieces) amax = fmaxf(amax, fmaxf(fabsf(x0), fabsf(x1)));
+                                h2[e] = __floats2half2_rn(x0, x1);
+                                const float2 hf = __half22float2(h2[e]);
+                                l2[e] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
                             }
-                            continue;
-                        }
-#pragma unroll
-                        for (int part = 0; part < 2; ++part) {                     // hi chunk, then lo chunk
-                            uint4* dst = stage_begin();
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                __half h8[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    float x = sum[64 * ch + 8 * j + e];
-                                    if (p.split_relu) x = fmaxf(x, 0.0f);
-                                    __half hi, lo;
-                                    int f2 = 0;
-                                    split_f16(x, p.out_scale, hi, lo, f2);
-                                    if (part == 0 && row_ok && col0 + 8 * j + e < p.N) flag |= f2;
-                                    h8[e] = part == 0 ? hi : lo;
-                                }
-                                dst[j ^ (lane & 7)] = *reinterpret_cast<const uint4*>(h8);
+                            if (j < pieces) {
+                                const int slot = is_tail ? j : (j ^ (lane & 7));
+                                dh[slot] = *reinterpret_cast<const uint4*>(h2);
+                                dl[slot] = *reinterpret_cast<const uint4*>(l2);
                             }
-                            stage_end(part == 0 ? &map_yh : &map_yl, col0);
                         }
+                        if (row_ok && !(amax <= 65000.0f)) flag |= 4;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(is_tail ? &map_yh_tail : &map_yh, stg_u32, col0, row0);
+                            tma_store_2d(is_tail ? &map_yl_tail : &map_yl, stg_u32 + LIN_STG_BYTES, col0, row0);
+                        }
+                        stg_buf = 0;
                     }
                 }
             } else if (row < p.n_rows) {
@@ -537,16 +560,16 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D map of an output tensor for the staged TMA stores: boxes of 32 rows x 128 bytes, SWIZZLE_128B
-static int make_store_map(CUtensorMap* map, void* base, bool fp16, int64_t rows, int64_t cols, int64_t ld) {
+static int make_store_map(CUtensorMap* map, void* base, bool fp16, int64_t rows, int64_t cols, int64_t ld, int box_cols = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const int es = fp16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * es};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+    cuuint32_t box[2] = {(cuuint32_t)(box_cols ? box_cols : 128 / es), 32};      // box_cols: narrow unswizzled tail chunk
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled (store map) failed with CUresult %d", (int)r);
     return NFK_OK;
@@ -647,13 +670,19 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     if ((rc = tc::make_map(&mw_hi, w_hi, out_features, in_features, ldw, bn / CL))) return rc;
     if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn / CL))) return rc;
     // staged TMA stores need 16-byte aligned bases and row pitches for every requested output
-    CUtensorMap my = mw_hi, myh = mw_hi, myl = mw_hi;      // placeholders when an output is absent (never dereferenced)
+    CUtensorMap my = mw_hi, myh = mw_hi, myl = mw_hi, myt = mw_hi, myht = mw_hi, mylt = mw_hi;   // placeholders (never dereferenced)
     p.tma_store = (!Y || (aligned16(Y) && ldy % 4 == 0)) && (!y_hi || (aligned16(y_hi) && aligned16(y_lo) && lds % 8 == 0)) ? 1 : 0;
     if (p.tma_store) {
         const int64_t pn = p.split_n < out_features ? p.split_n : out_features;
         if (Y && (rc = tc::make_store_map(&my, Y, false, n_rows, out_features, ldy))) return rc;
         if (y_hi && (rc = tc::make_store_map(&myh, y_hi, true, n_rows, pn, lds))) return rc;
         if (y_hi && (rc = tc::make_store_map(&myl, y_lo, true, n_rows, pn, lds))) return rc;
+        // the second column half of a tile is bn - 128 wide: what does not fill a 32- (fp32) / 64-column (fp16) chunk leaves
+        // through narrow chunks
+        const int w1 = bn > 128 ? bn - 128 : bn;
+        if (Y && w1 % 32 && (rc = tc::make_store_map(&myt, Y, false, n_rows, out_features, ldy, w1 % 32))) return rc;
+        if (y_hi && w1 % 64 && (rc = tc::make_store_map(&myht, y_hi, true, n_rows, pn, lds, w1 % 64))) return rc;
+        if (y_hi && w1 % 64 && (rc = tc::make_store_map(&mylt, y_lo, true, n_rows, pn, lds, w1 % 64))) return rc;
     }
 
     static bool attr_set = false;
@@ -678,8 +707,8 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, p)
-                               : cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, p);
+    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, myt, myht, mylt, p)
+                               : cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, myt, myht, mylt, p);
     if (le != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(linear_f16x3_kernel, cluster %d): %s", CL, cudaGetErrorString(le));
     return check_launch("linear_f16x3_kernel");
 }
