@@ -25,6 +25,7 @@ struct FusedParams {
     float* y;               // coupling output [n_rows, ldy]; identity columns are written by the caller
     const int32_t* t_cols;  // [d_t] column of transformed feature j, or null: feature j lives in column t_col0 + j
     int t_col0;
+    int tma_y;              // y goes out through staged TMA stores (consecutive columns, 16-byte aligned)
     float* lad_accum;       // [n_rows] running log|det| (read-modify-write) or null
     int32_t* flags;
     int64_t ldx, ldy, n_rows;
@@ -59,6 +60,10 @@ struct FusedCfg {
     static constexpr int TILE_FEATURES = EWG * FPT;
     static constexpr int TILE_COLS = EWG * HALF_COLS;           // packed weight rows per tile
     static constexpr int BN = (TILE_COLS + 15) / 16 * 16;       // MMA N (the pad columns compute the next feature's first rows, unused)
+    // outputs leave through shared memory, YG column tiles at a time, so that a staged row (YG * TILE_FEATURES floats) is a
+    // multiple of 16 bytes -- what a TMA store needs
+    static constexpr int YG = TILE_FEATURES % 4 == 0 ? 1 : (TILE_FEATURES % 2 == 0 ? 2 : 4);
+    static constexpr int YROW = YG * TILE_FEATURES;             // floats per staged row
     static_assert(FPT >= 1 && BN <= BN_MAX, "unsupported bin count for the fused kernel");
 };
 
@@ -194,7 +199,7 @@ template <int NB, bool TAILS, int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                         const FusedParams p) {
+                         const __grid_constant__ CUtensorMap map_y, const FusedParams p) {
     using Cfg = FusedCfg<NB, TAILS>;
     constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HALF_COLS, BN = Cfg::BN, TILE = Cfg::TILE_COLS;
     constexpr bool PAIR = MODE == 3;
@@ -217,6 +222,11 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     // 40 % of the epilogue warps' samples)
     float* s_bias = reinterpret_cast<float*>(smem_gen + STAGES * STAGE_BYTES + 256 + 512 * EWG);   // [2][BN_MAX]
     const uint32_t bar_bfull = bars + 16 * NST + 48, bar_bempty = bars + 16 * NST + 64;
+    // transformed outputs of YG consecutive column tiles, [2 buffers][128 rows][YROW] fp32, sent out by one TMA store per
+    // group: a row-per-thread st.global of 5 floats per tile touched 32 sectors per instruction with 4 useful bytes each
+    constexpr int YG = Cfg::YG, YROW = Cfg::YROW;
+    constexpr int Y_OFF = STAGES * STAGE_BYTES + 256 + 512 * EWG + 2 * BN_MAX * 4;
+    float* s_y = reinterpret_cast<float*>(smem_gen + Y_OFF);
 
     uint32_t tid_x;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));      // volatile: not re-read (S2R) inside the tile loop
@@ -371,6 +381,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         int acc = 0; uint32_t acc_phase = 0;
         int flag = 0;
         int bslot = 0; uint32_t bphase = 0;
+        int ybuf = 0;
         for (int mb = first_block; mb < num_blocks; mb += block_step) {
             const int m = mb * CL + cta_rank;
             const int64_t row = (int64_t)m * BM + q * 32 + lane;
@@ -447,11 +458,34 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 {
                     float yy[FPT], ll[FPT];
                     rqs_eval_multi<NB, TAILS, FPT, MP>(p.sp, p.inverse != 0, xin, sum, yy, ll, flag);
+                    if (p.tma_y) {
+                        float* dst = s_y + ((size_t)ybuf * BM + q * 32 + lane) * YROW + (n % YG) * Cfg::TILE_FEATURES + half * FPT;
 #pragma unroll
-                    for (int f = 0; f < FPT; ++f) {
-                        if (row_ok && j0 + f < p.d_t) {
-                            p.y[row * p.ldy + col[f]] = yy[f];
-                            lad_row += ll[f];
+                        for (int f = 0; f < FPT; ++f) {
+                            dst[f] = yy[f];
+                            if (row_ok && j0 + f < p.d_t) lad_row += ll[f];
+                        }
+                        if (n % YG == YG - 1 || n == p.num_n_tiles - 1) {
+                            const bool issuer = warp == 4 && lane == 0;
+                            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the other buffer is free again
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            asm volatile("bar.sync 2, %0;" ::"n"(128 * EWG) : "memory");
+                            if (issuer) {
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                                 reinterpret_cast<uint64_t>(&map_y)),
+                                             "r"(smem_base + Y_OFF + ybuf * BM * YROW * 4), "r"(p.t_col0 + (n / YG) * YROW), "r"(m * BM)
+                                             : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                            ybuf ^= 1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int f = 0; f < FPT; ++f) {
+                            if (row_ok && j0 + f < p.d_t) {
+                                p.y[row * p.ldy + col[f]] = yy[f];
+                                lad_row += ll[f];
+                            }
                         }
                     }
                 }
@@ -472,6 +506,7 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 asm volatile("bar.sync 1, %0;" ::"n"(128 * EWG) : "memory");
             }
         }
+        if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging outlives its stores
         if (flag && p.flags) atomicOr(p.flags, flag);
     }
 
@@ -503,7 +538,12 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     if ((rc = make_map(&mw_hi, w_hi, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
     if ((rc = make_map(&mw_lo, w_lo, packed_rows, p.K, ldw, Cfg::BN / CL))) return rc;
     p.num_n_tiles = (p.d_t + Cfg::TILE_FEATURES - 1) / Cfg::TILE_FEATURES;
-    constexpr int smem = SMEM_BYTES + 512 * EWG + 2 * BN_MAX * 4;
+    constexpr int smem = SMEM_BYTES + 512 * EWG + 2 * BN_MAX * 4 + 2 * BM * Cfg::YROW * 4;
+    static_assert(smem <= 232448, "fused kernel shared memory");
+    // y through staged TMA stores: consecutive transformed columns and 16-byte aligned rows / first column
+    CUtensorMap my = mw_hi;
+    p.tma_y = (!p.t_cols && p.t_col0 % 4 == 0 && p.ldy % 4 == 0 && aligned16(p.y)) ? 1 : 0;
+    if (p.tma_y && (rc = make_out_map(&my, p.y, p.n_rows, p.t_col0 + p.d_t, p.ldy, Cfg::YROW, BM))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -522,7 +562,7 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, MODE>, ma_hi, ma_lo, mw_hi, mw_lo, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, MODE>, ma_hi, ma_lo, mw_hi, mw_lo, my, p);
     if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(rq_coupling_final_kernel, cluster %d): %s", CL, cudaGetErrorString(e));
     return check_launch("rq_coupling_final_kernel");
 }
