@@ -7,6 +7,8 @@ One "step" = one Flow.log_prob pass over one synthetic Gaussian batch of R rows 
 owns R rows and a replica of the weights; the only collective is the all-gather of per-sample log-probs).  Prints
 ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for what each key means.
 """
+import os
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 import argparse
 import json
 import os
