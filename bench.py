@@ -108,6 +108,31 @@ def cpu_oracle_rate(flow, budget_s=12.0, chunk=2048, max_rows=1 << 15):
     return rows / dt, rows, torch.get_num_threads()
 
 
+def torch_cuda_rate(flow, dev, budget_s=6.0, chunk=1 << 14, max_rows=1 << 18):
+    """SURVEY.md section 8(d) "reference-CUDA baseline": the same restatement of the reference path (oracle/, plain torch ops,
+    true-fp32 matmuls) with weights and data on the GPU, chunked so the [chunk, d_t * 23] parameter tensor the reference
+    materialises fits.  A reported context figure, like cpu_baseline; none of this package's kernels run here."""
+    from oracle import flow_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = {k: v.detach().to(dev).clone() for k, v in flow.state_dict().items()}
+    spec = O.nsf_spec(LAYERS, num_bins=BINS, tail_bound=3.0)
+    g = torch.Generator(device=dev).manual_seed(123)
+    x = torch.randn(chunk, FEATURES, device=dev, generator=g)
+    with torch.no_grad():
+        O.flow_log_prob(sd, spec, x[:1024])
+        torch.cuda.synchronize()
+        rows, t0 = 0, time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        while rows < max_rows and time.perf_counter() - t0 < budget_s:
+            O.flow_log_prob(sd, spec, x)
+            rows += chunk
+            torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+    return rows / (e0.elapsed_time(e1) * 1e-3), rows
+
+
 def spline_hbm_roofline(dev, peaks, rows=1 << 20, d_t=32, bins=8, iters=10):
     """The HBM-bound spline segment (BASELINE configs[1] shape): conditioner output [rows, d_t*(3K-1)] resident in HBM ->
     nfk_rqs_rows.  Algorithmic bytes = 4*(M+2) per transformed element + 4 per identity element copied (read+write)."""
@@ -299,6 +324,12 @@ def run_native(args):
         result["roofline_spline"] = spline_hbm_roofline(dev, peaks)
     # ---- CPU baseline (oracle port) on this box's host cores ---------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
+        try:
+            rate, sample_rows = torch_cuda_rate(flow, dev)
+            result["torch_cuda_baseline"] = {"value": rate, "unit": "samples/s", "kind": "port", "sample":
+                                             "%d rows in chunks of 16384, torch eager fp32 (allow_tf32 off) on the same GPU" % sample_rows}
+        except Exception as exc:     # a context figure only: never let it take the bench line down
+            result["torch_cuda_baseline"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
         rate, sample_rows, threads = cpu_oracle_rate(flow.cpu(), budget_s=args.ref_budget, max_rows=args.ref_rows)
         result["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                                   "sample": "%d rows of the same workload in chunks of 2048" % sample_rows}

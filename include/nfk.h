@@ -104,6 +104,9 @@ int nfk_linear_f16x3(const void* a_hi, const void* a_lo, int64_t lda, int32_t a_
                      int64_t n_rows, int32_t in_features, int32_t out_features, int32_t* flags, void* stream);
 /* hi[n, j], lo[n, j] = fp16 split pair of pre(x[n*ldx + j]) * 2^scale_exp, pre = relu if `relu`: weights (once per parameter
  * update), tensors entering a tensor-core chain from outside, the transformed half of a coupling output. */
+/* *out = max(*out, max |x[n, j]|) over an n_rows x n_cols matrix (NaNs skipped); *out must be >= 0 on entry.  Used to pick the
+ * power-of-two exponent of a weight's split pair. */
+int nfk_absmax(const float* x, int64_t ldx, int64_t n_rows, int32_t n_cols, float* out, void* stream);
 int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int relu, int32_t scale_exp, void* hi, void* lo, int64_t ldo,
                   int64_t n_rows, int32_t* flags, void* stream);
 

@@ -155,6 +155,29 @@ extern "C" int nfk_add_const(float* lad_accum, float c, int64_t n_rows, void* st
     return check_launch("add_const_kernel");
 }
 
+// max |x| of a (possibly strided) matrix into *out (a non-negative float, so its bit pattern orders like an int):
+// *out must hold 0.0f on entry.  NaNs are skipped (fmaxf).
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t ldx, int64_t n_rows, int n_cols, float* out) {
+    float m = 0.0f;
+    const int64_t total = n_rows * n_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n_cols;
+        m = fmaxf(m, fabsf(x[r * ldx + (i - r * n_cols)]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+extern "C" int nfk_absmax(const float* x, int64_t ldx, int64_t n_rows, int32_t n_cols, float* out, void* stream) {
+    NFK_REQUIRE(n_rows >= 0 && n_cols >= 0, "bad sizes");
+    NFK_REQUIRE(out, "NULL pointer");
+    if (n_rows == 0 || n_cols == 0) return NFK_OK;
+    NFK_REQUIRE(x, "NULL pointer");
+    absmax_kernel<<<grid_for(n_rows * n_cols, kThreads), kThreads, 0, (cudaStream_t)stream>>>(x, ldx, n_rows, n_cols, out);
+    return check_launch("absmax_kernel");
+}
+
 extern "C" int nfk_fill(float* dst, float value, int64_t n, void* stream) {
     NFK_REQUIRE(n >= 0, "bad size");
     if (n == 0) return NFK_OK;

@@ -193,7 +193,10 @@ def weight_exp(w):
     """Power-of-two exponent that lifts max |w| to 2^14: the whole matrix, including the lo parts, stays clear of fp16's
     subnormals and of its overflow."""
     import math
-    amax = float(w.detach().abs().max()) if w.numel() else 0.0
+    w = _rows2d(w.detach(), "w")
+    out = fill_(torch.empty(1, dtype=torch.float32, device=w.device), 0.0)
+    N.check(N.lib().nfk_absmax(w.data_ptr(), w.stride(0), w.shape[0], w.shape[1], out.data_ptr(), N.stream()))
+    amax = float(out.item())
     if not (amax > 0.0) or not math.isfinite(amax):
         return 0
     return max(-40, min(40, 14 - math.ceil(math.log2(amax))))

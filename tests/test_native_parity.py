@@ -497,3 +497,25 @@ def test_autoregressive_rq_transform_cfg4(cuda_device):
     finally:
         config.fuse_coupling = True
     assert rel_err(y2, y) <= 2e-5
+
+
+@torch.no_grad()
+def test_fp16_range_overflow_is_reported_not_silent(cuda_device):
+    """Activations beyond the fp16 split range (|a| * 2^config.activation_exp > 65000) raise through the flag word; a lower
+    exponent accepts them and still meets parity."""
+    from nflows_b200 import kernels as K
+    torch.manual_seed(3)
+    lu = T.LULinear(16).eval()
+    x = torch.randn(64, 16) * 300.0
+    x[5, 3] = 4000.0                                    # 4000 * 2^6 overflows fp16
+    want = lu(x)[0]
+    lu = lu.to(cuda_device)
+    with pytest.raises(K.Float16RangeError):
+        lu(x.to(cuda_device))
+    old = config.activation_exp
+    config.activation_exp = 2
+    try:
+        y, _ = lu(x.to(cuda_device))
+    finally:
+        config.activation_exp = old
+    assert rel_err(y.cpu(), want) <= TOL
