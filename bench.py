@@ -311,8 +311,8 @@ def run_native(args):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             t = json.load(open(tpath))
-            if t.get("kernel") == tag and t.get("rows_per_launch") == rows_k // count:
-                traffic = t["dram_bytes_per_launch"]
+            if t.get("kernel") == tag and "dram_bytes_per_row" in t:
+                traffic = t["dram_bytes_per_row"] * (rows_k // count)     # per launch, like `achieved`
         result["roofline"] = {"kernel": tag, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                               "frac": achieved / peak, "traffic": traffic, "launches": count,
                               "avg_launch_ms": tms / count, "share_of_step": tms / ms_total,
@@ -348,9 +348,13 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per reference step")
     ap.add_argument("--ref-rows", type=int, default=1 << 15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-rows", type=int, default=0, help="override config.{trunk,affine,coupling}_block_rows (experiments)")
     ap.add_argument("--no-spline-roofline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="rows per host->device chunk of the end-to-end leg")
     args = ap.parse_args()
+    if args.block_rows:
+        from nflows_b200 import config
+        config.trunk_block_rows = config.affine_block_rows = config.coupling_block_rows = args.block_rows
     if args.impl == "reference":
         run_reference(args)
     else:

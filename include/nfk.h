@@ -82,7 +82,7 @@ int nfk_rqs_rows(const NfkSplineDesc* desc, int inverse, const float* x, int64_t
 /* Y[n, o] = post( sum_k pre(X[n, k]) * W[o, k] + bias[o] ) + R[n, o]
  * with pre = relu if relu_in, post = relu if relu_out, R optional (NULL).  W is [out, in] row-major exactly as
  * torch.nn.Linear stores it (F.linear: nn/nets/resnet.py:44-49,94-99; transforms/lu.py:65-66).  fp32 accumulate
- * with fp32-equivalent operand precision (SIMT FFMA path, or split-TF32 tcgen05 path). */
+ * with fp32-equivalent operand precision (SIMT FFMA path, or split-fp16 tcgen05 path). */
 int nfk_linear(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, const float* R,
                int64_t ldr, float* Y, int64_t ldy, int64_t n_rows, int32_t in_features, int32_t out_features,
                int relu_in, int relu_out, void* stream);

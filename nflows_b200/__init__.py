@@ -21,10 +21,13 @@ class _Config:
     activation_exp = 6
     #: rows per sub-block of a dense-layer chain: intermediates of a sub-block (split pairs, hidden activations) stay
     #: resident in the 126 MB L2 between consecutive kernels instead of round-tripping through HBM
-    #: (measured r1: sub-blocks of 8-16 K rows are SLOWER -- 1-wave launches pay prologue/launch overhead -- so the default
-    #: keeps whole 256 K-row blocks; the knob stays for a future persistent / graph-captured executor)
-    trunk_block_rows = 1 << 18
-    affine_block_rows = 1 << 18
+    #: (measured r1: sub-blocks of 8-16 K rows are SLOWER -- 1-wave launches pay prologue/launch overhead; 256 K / 512 K / 1 M
+    #: rows: 307 / 303 / 303 ms per cfg-3 step -- so the default keeps 512 K-row blocks, which also bounds the temporaries;
+    #: the knob stays for a future persistent / graph-captured executor)
+    trunk_block_rows = 1 << 19
+    affine_block_rows = 1 << 19
+    #: rows per (trunk, fused final layer + spline) round of a coupling on the fused path
+    coupling_block_rows = 1 << 19
 
 
 config = _Config()

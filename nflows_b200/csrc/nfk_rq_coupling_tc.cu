@@ -4,7 +4,7 @@
 // the transformed features and the per-row log|det| evaluated by the epilogue warps straight from the accumulators.
 // The [B, d_t*M] parameter tensor the reference materialises (37.8 GB per layer at B = 2^20) never exists.
 //
-// Same machinery as nfk_linear_tc.cu (TMA-fed split-TF32 operands, partial sums drained from TMEM into registers);
+// Same machinery as nfk_linear_tc.cu (TMA-fed fp16 split-pair operands, partial sums drained from TMEM into registers);
 // what differs:
 //   * the packed weight has MP = roundup(M, 8) rows per transformed feature (zero padded), so a tile of BN = 2*FPT*MP
 //     columns holds whole features and each accumulate/epilogue thread ends a tile owning ALL parameters of FPT features

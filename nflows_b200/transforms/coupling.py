@@ -138,7 +138,7 @@ class CouplingTransform(Transform):
         if pair is None:
             pair = K.Pair16.empty(n, self.features, D.act_exp(), x.device)
             K.split_f16(x[:, :d_id], pair.exp, out=pair.cols(0, d_id), flags=flags)
-        block = 1 << 18
+        block = max(128, int(config.coupling_block_rows))
         for r0 in range(0, n, block):
             r1 = min(n, r0 + block)
             xs = x[r0:r1]
@@ -194,7 +194,7 @@ class CouplingTransform(Transform):
             if self._all_cols is None or self._all_cols.device != inputs.device:
                 self._all_cols = torch.arange(self.features, dtype=torch.int32, device=inputs.device)
             K.gather_cols(inputs, self._all_cols, out=outputs)
-            block = 1 << 18
+            block = max(128, int(config.coupling_block_rows))
             for r0 in range(0, n, block):
                 r1 = min(n, r0 + block)
                 state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, flags=flags)
