@@ -122,6 +122,9 @@ int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int relu, int32_t
  * CompositeTransform arranges: no index load in front of every x load).
  * Writes y[n, t_cols[j]] for every transformed feature and adds the row's log|det| to lad_accum.  y may be x itself
  * (in place: the identity columns then need no copy); otherwise the caller fills the identity columns of y.
+ * Output: EITHER y (fp32; y_hi = y_lo = NULL) OR, with y = NULL, the fp16 split pair y_hi / y_lo (row pitch lds, exponent y_exp)
+ * of the same columns -- what the tensor-core layer that consumes the coupling output next reads (needs t_cols = NULL,
+ * t_col0 a multiple of 8); x is left untouched in that mode.
  * nfk_rq_coupling_final_supported says whether an instance exists for (num_bins, tails, hidden_features, lda); otherwise
  * use nfk_linear* + nfk_rqs_rows. */
 int nfk_rq_coupling_final_supported(int32_t num_bins, int32_t linear_tails, int32_t hidden_features, int64_t lda);
@@ -129,8 +132,9 @@ int32_t nfk_rq_coupling_final_padded_params(int32_t num_bins, int32_t linear_tai
 int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int inverse, const void* a_hi, const void* a_lo, int64_t lda,
                                int32_t a_exp, const void* wp_hi, const void* wp_lo, int64_t ldw, int32_t w_exp,
                                const float* bias_packed, int32_t hidden_features, const float* x, int64_t ldx,
-                               const int32_t* t_cols, int32_t t_col0, int32_t d_t, float* y, int64_t ldy, float* lad_accum,
-                               int64_t n_rows, int32_t* flags, void* stream);
+                               const int32_t* t_cols, int32_t t_col0, int32_t d_t, float* y, int64_t ldy, void* y_hi,
+                               void* y_lo, int64_t lds, int32_t y_exp, float* lad_accum, int64_t n_rows, int32_t* flags,
+                               void* stream);
 
 /* ---- row-wise elementwise transforms -------------------------------------------------------------------- */
 /* out[n, j] = x[n*ldx + cols[j]] (identity_split gather, coupling.py:82; Permutation._permute,

@@ -48,7 +48,8 @@ _SIGNATURES = {
     "nfk_rq_coupling_final_supported": (c_int, [c_int32, c_int32, c_int32, c_int64]),
     "nfk_rq_coupling_final_padded_params": (c_int32, [c_int32, c_int32]),
     "nfk_rq_coupling_final_f16x3": (c_int, [POINTER(NfkSplineDesc), c_int, _P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P,
-                                            c_int32, _P, c_int64, _P, c_int32, c_int32, _P, c_int64, _P, c_int64, _P, _P]),
+                                            c_int32, _P, c_int64, _P, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, c_int32, _P,
+                                            c_int64, _P, _P]),
     "nfk_gather_cols": (c_int, [_P, c_int64, _P, c_int32, _P, c_int64, c_int64, _P]),
     "nfk_actnorm": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, c_float, c_int64, c_int32, c_int, _P]),
     "nfk_add_const": (c_int, [_P, c_float, c_int64, _P]),

@@ -26,6 +26,8 @@ struct FusedParams {
     const int32_t* t_cols;  // [d_t] column of transformed feature j, or null: feature j lives in column t_col0 + j
     int t_col0;
     int tma_y;              // y goes out through staged TMA stores (consecutive columns, 16-byte aligned)
+    int pair_only;          // write the fp16 split pair of the outputs (through map_yh / map_yl) INSTEAD of fp32 y
+    float out_scale;        // 2^e of that pair
     float* lad_accum;       // [n_rows] running log|det| (read-modify-write) or null
     int32_t* flags;
     int64_t ldx, ldy, n_rows;
@@ -64,6 +66,10 @@ struct FusedCfg {
     // multiple of 16 bytes -- what a TMA store needs
     static constexpr int YG = TILE_FEATURES % 4 == 0 ? 1 : (TILE_FEATURES % 2 == 0 ? 2 : 4);
     static constexpr int YROW = YG * TILE_FEATURES;             // floats per staged row
+    // pair-only output (fp16 hi / lo instead of fp32 y): groups of YG16 tiles make a staged row a multiple of 16 bytes
+    static constexpr int YG16 = TILE_FEATURES % 8 == 0 ? 1 : (TILE_FEATURES % 4 == 0 ? 2 : (TILE_FEATURES % 2 == 0 ? 4 : 8));
+    static constexpr int YROW16 = YG16 * TILE_FEATURES;         // halfs per staged row
+    static_assert(2 * YROW16 * 2 <= 2 * YROW * 4, "pair staging must fit the y staging area");
     static_assert(FPT >= 1 && BN <= BN_MAX, "unsupported bin count for the fused kernel");
 };
 
@@ -199,7 +205,8 @@ template <int NB, bool TAILS, int MODE>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                         const __grid_constant__ CUtensorMap map_y, const FusedParams p) {
+                         const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yh,
+                         const __grid_constant__ CUtensorMap map_yl, const FusedParams p) {
     using Cfg = FusedCfg<NB, TAILS>;
     constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HALF_COLS, BN = Cfg::BN, TILE = Cfg::TILE_COLS;
     constexpr bool PAIR = MODE == 3;
@@ -458,7 +465,46 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 {
                     float yy[FPT], ll[FPT];
                     rqs_eval_multi<NB, TAILS, FPT, MP>(p.sp, p.inverse != 0, xin, sum, yy, ll, flag);
-                    if (p.tma_y) {
+                    if (p.pair_only) {
+                        // the consumer of this coupling's output is a tensor-core layer: it reads the fp16 split pair, so that
+                        // is all that is written (no fp32 y, no separate split pass).  One staging area (hi rows, then lo
+                        // rows), reused per group of YG16 tiles: the issuer makes sure the previous group's stores have
+                        // read it before the first write of a group.
+                        constexpr int YG16 = Cfg::YG16, YROW16 = Cfg::YROW16;
+                        const bool issuer = warp == 4 && lane == 0;
+                        if (n % YG16 == 0) {
+                            if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            asm volatile("bar.sync 2, %0;" ::"n"(128 * EWG) : "memory");
+                        }
+                        __half* sh = reinterpret_cast<__half*>(s_y);
+                        __half* sl = sh + BM * YROW16;
+                        const int off = (q * 32 + lane) * YROW16 + (n % YG16) * Cfg::TILE_FEATURES + half * FPT;
+#pragma unroll
+                        for (int f = 0; f < FPT; ++f) {
+                            __half hi, lo;
+                            int f2 = 0;
+                            split_f16(yy[f], p.out_scale, hi, lo, f2);
+                            sh[off + f] = hi;
+                            sl[off + f] = lo;
+                            if (row_ok && j0 + f < p.d_t) { lad_row += ll[f]; flag |= f2; }
+                        }
+                        if (n % YG16 == YG16 - 1 || n == p.num_n_tiles - 1) {
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            asm volatile("bar.sync 2, %0;" ::"n"(128 * EWG) : "memory");
+                            if (issuer) {
+                                const int c0 = p.t_col0 + (n / YG16) * YROW16;
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                                 reinterpret_cast<uint64_t>(&map_yh)),
+                                             "r"(smem_base + Y_OFF), "r"(c0), "r"(m * BM)
+                                             : "memory");
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                                 reinterpret_cast<uint64_t>(&map_yl)),
+                                             "r"(smem_base + Y_OFF + BM * YROW16 * 2), "r"(c0), "r"(m * BM)
+                                             : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                        }
+                    } else if (p.tma_y) {
                         float* dst = s_y + ((size_t)ybuf * BM + q * 32 + lane) * YROW + (n % YG) * Cfg::TILE_FEATURES + half * FPT;
 #pragma unroll
                         for (int f = 0; f < FPT; ++f) {
@@ -529,7 +575,7 @@ static int cluster_mode() {
 
 template <int NB, bool TAILS, int MODE>
 static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const __half* w_hi, const __half* w_lo, int64_t ldw,
-                           FusedParams& p, cudaStream_t st) {
+                           FusedParams& p, cudaStream_t st, __half* pair_hi, __half* pair_lo, int64_t pair_lds) {
     using Cfg = FusedCfg<NB, TAILS>;
     constexpr int CL = MODE == 1 ? 1 : 2;
     const int packed_rows = p.d_t * Cfg::MP;
@@ -542,8 +588,15 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     static_assert(smem <= 232448, "fused kernel shared memory");
     // y through staged TMA stores: consecutive transformed columns and 16-byte aligned rows / first column
     CUtensorMap my = mw_hi;
-    p.tma_y = (!p.t_cols && p.t_col0 % 4 == 0 && p.ldy % 4 == 0 && aligned16(p.y)) ? 1 : 0;
+    p.tma_y = (p.y && !p.t_cols && p.t_col0 % 4 == 0 && p.ldy % 4 == 0 && aligned16(p.y)) ? 1 : 0;
     if (p.tma_y && (rc = make_out_map(&my, p.y, p.n_rows, p.t_col0 + p.d_t, p.ldy, Cfg::YROW, BM))) return rc;
+    CUtensorMap myh = mw_hi, myl = mw_hi;
+    if (p.pair_only) {
+        NFK_REQUIRE(!p.t_cols && p.t_col0 % 8 == 0 && pair_lds % 8 == 0 && aligned16(pair_hi) && aligned16(pair_lo),
+                    "pair-only output needs consecutive transformed columns starting at a multiple of 8 and 16-byte aligned rows");
+        if ((rc = make_out_map16(&myh, pair_hi, p.n_rows, p.t_col0 + p.d_t, pair_lds, Cfg::YROW16, BM))) return rc;
+        if ((rc = make_out_map16(&myl, pair_lo, p.n_rows, p.t_col0 + p.d_t, pair_lds, Cfg::YROW16, BM))) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -562,18 +615,18 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, MODE>, ma_hi, ma_lo, mw_hi, mw_lo, my, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rq_coupling_final_kernel<NB, TAILS, MODE>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, p);
     if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(rq_coupling_final_kernel, cluster %d): %s", CL, cudaGetErrorString(e));
     return check_launch("rq_coupling_final_kernel");
 }
 
 template <int NB, bool TAILS>
 static int launch_fused(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const __half* w_hi, const __half* w_lo, int64_t ldw,
-                        FusedParams& p, cudaStream_t st) {
+                        FusedParams& p, cudaStream_t st, __half* pair_hi, __half* pair_lo, int64_t pair_lds) {
     switch (cluster_mode()) {
-        case 1: return launch_fused_cl<NB, TAILS, 1>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
-        case 2: return launch_fused_cl<NB, TAILS, 2>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
-        default: return launch_fused_cl<NB, TAILS, 3>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st);
+        case 1: return launch_fused_cl<NB, TAILS, 1>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st, pair_hi, pair_lo, pair_lds);
+        case 2: return launch_fused_cl<NB, TAILS, 2>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st, pair_hi, pair_lo, pair_lds);
+        default: return launch_fused_cl<NB, TAILS, 3>(ma_hi, ma_lo, w_hi, w_lo, ldw, p, st, pair_hi, pair_lo, pair_lds);
     }
 }
 
@@ -596,7 +649,8 @@ extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int invers
                                           int64_t lda, int32_t a_exp, const void* wp_hi_, const void* wp_lo_, int64_t ldw,
                                           int32_t w_exp, const float* bias_packed, int32_t hidden_features, const float* x,
                                           int64_t ldx, const int32_t* t_cols, int32_t t_col0, int32_t d_t, float* y,
-                                          int64_t ldy, float* lad_accum, int64_t n_rows, int32_t* flags, void* stream) {
+                                          int64_t ldy, void* y_hi, void* y_lo, int64_t lds, int32_t y_exp, float* lad_accum,
+                                          int64_t n_rows, int32_t* flags, void* stream) {
     const __half* a_hi = (const __half*)a_hi_; const __half* a_lo = (const __half*)a_lo_;
     const __half* wp_hi = (const __half*)wp_hi_; const __half* wp_lo = (const __half*)wp_lo_;
     tc::FusedParams p;
@@ -604,7 +658,9 @@ extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int invers
     if (rc) return rc;
     NFK_REQUIRE(n_rows >= 0 && d_t >= 1 && hidden_features >= 1, "bad sizes");
     if (n_rows == 0) return NFK_OK;
-    NFK_REQUIRE(a_hi && a_lo && wp_hi && wp_lo && bias_packed && x && y, "NULL pointer");
+    NFK_REQUIRE(a_hi && a_lo && wp_hi && wp_lo && bias_packed && x, "NULL pointer");
+    NFK_REQUIRE((y != nullptr) != (y_hi != nullptr), "give either y (fp32 outputs) or y_hi / y_lo (their fp16 split pair)");
+    NFK_REQUIRE((y_hi == nullptr) == (y_lo == nullptr) && y_exp >= -60 && y_exp <= 60, "bad pair output");
     NFK_REQUIRE(t_cols || t_col0 >= 0, "t_cols is NULL and t_col0 is negative");
     NFK_REQUIRE(aligned16(bias_packed), "bias_packed must be 16-byte aligned");
     NFK_REQUIRE(nfk_rq_coupling_final_supported(desc->num_bins, desc->linear_tails, hidden_features, lda) && ldw % 8 == 0,
@@ -615,6 +671,7 @@ extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int invers
     p.bias = bias_packed; p.x = x; p.y = y; p.t_cols = t_cols; p.t_col0 = t_col0; p.lad_accum = lad_accum; p.flags = flags;
     p.ldx = ldx; p.ldy = ldy; p.n_rows = n_rows; p.K = hidden_features; p.d_t = d_t; p.inverse = inverse;
     p.acc_scale = ldexpf(1.0f, a_exp + w_exp); p.inv_acc_scale = ldexpf(1.0f, -(a_exp + w_exp));
+    p.pair_only = y_hi ? 1 : 0; p.out_scale = ldexpf(1.0f, y_exp);
     p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
     CUtensorMap ma_hi, ma_lo;
     if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, hidden_features, lda, tc::BM))) return rc;
@@ -622,8 +679,8 @@ extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int invers
     cudaStream_t st = (cudaStream_t)stream;
     const bool tails = desc->linear_tails != 0;
 #define NFK_FUSED(NB)                                                                                       \
-    return tails ? tc::launch_fused<NB, true>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st)                        \
-                 : tc::launch_fused<NB, false>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st)
+    return tails ? tc::launch_fused<NB, true>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st, (__half*)y_hi, (__half*)y_lo, lds)   \
+                 : tc::launch_fused<NB, false>(ma_hi, ma_lo, wp_hi, wp_lo, ldw, p, st, (__half*)y_hi, (__half*)y_lo, lds)
     switch (desc->num_bins) {
         case 4: NFK_FUSED(4);
         case 8: NFK_FUSED(8);

@@ -214,6 +214,7 @@ __device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __ha
 // host helpers (nfk_linear_tc.cu)
 int make_map(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t ld, int box_rows);
 int make_out_map(CUtensorMap* map, float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
+int make_out_map16(CUtensorMap* map, __half* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
 int sm_count();
 
 }  // namespace tc

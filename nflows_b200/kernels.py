@@ -252,9 +252,10 @@ def rq_coupling_final_padded_params(num_bins, tails):
     return int(N.load().nfk_rq_coupling_final_padded_params(int(num_bins), 1 if tails == "linear" else 0))
 
 
-def rq_coupling_final(desc, inverse, a, wp, bias_packed, x, t_cols, y, lad_accum, flags):
+def rq_coupling_final(desc, inverse, a, wp, bias_packed, x, t_cols, y, lad_accum, flags, y_pair=None):
     """Fused final conditioner layer + RQ spline + scatter + log|det| (one tcgen05 kernel).  a, wp: Pair16; y may be x.
-    t_cols: int32 column index tensor of the transformed features, or (first_column, count) when they are consecutive."""
+    t_cols: int32 column index tensor of the transformed features, or (first_column, count) when they are consecutive.
+    y_pair (with y=None): write the fp16 split pair of the outputs into this Pair16 (same shape as x) instead of fp32."""
     if isinstance(t_cols, tuple):
         cols_ptr, col0, d_t = 0, int(t_cols[0]), int(t_cols[1])
     else:
@@ -262,5 +263,7 @@ def rq_coupling_final(desc, inverse, a, wp, bias_packed, x, t_cols, y, lad_accum
     N.check(N.lib().nfk_rq_coupling_final_f16x3(
         ctypes.byref(desc), int(inverse), a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, wp.hi.data_ptr(),
         wp.lo.data_ptr(), wp.hi.stride(0), wp.exp, bias_packed.data_ptr(), a.shape[1], x.data_ptr(), x.stride(0),
-        cols_ptr, col0, d_t, y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
+        cols_ptr, col0, d_t, N.ptr(y), y.stride(0) if y is not None else 0, y_pair.hi.data_ptr() if y_pair is not None else 0,
+        y_pair.lo.data_ptr() if y_pair is not None else 0, y_pair.hi.stride(0) if y_pair is not None else 0,
+        y_pair.exp if y_pair is not None else 0, N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
     return y

@@ -144,7 +144,15 @@ class CompositeTransform(Transform):
                 x = K.gather_cols(x, want.cols(x.device))
                 layout, owned, carry["pair"] = want, True, None
             if layout is not None:
+                # does a folded affine run consume this leaf's output?  Then only the fp16 pair of it is ever read.
+                k = i + 1
+                lu_next = False
+                while k < len(leaves) and is_affine_leaf(leaves[k][0], x):
+                    lu_next = lu_next or leaves[k][0].__class__.__name__ in ("LULinear",)
+                    k += 1
+                carry["pair_only"] = lu_next
                 x = leaf._native_apply(x, lad, flags, inv, context, layout=layout, owned=owned, carry=carry)
+                carry["pair_only"] = False
                 owned = True
             elif leaf._native_ready(x, context):
                 x = leaf._native_apply(x, lad, flags, inv, context)

@@ -135,6 +135,9 @@ class CouplingTransform(Transform):
         chain = self.transform_net.dense_chain(context)
         n = x.shape[0]
         pair = carry["pair"] if carry is not None else None
+        # the next leaf is a folded affine run: it multiplies the fp16 pair of this output, never the fp32 values, so the
+        # fused kernel writes only the pair of the transformed block (x's transformed block is then stale and unread)
+        pair_only = bool(carry is not None and carry.get("pair_only") and config.fused_pair_only and d_id % 8 == 0)
         if pair is None:
             pair = K.Pair16.empty(n, self.features, D.act_exp(), x.device)
             K.split_f16(x[:, :d_id], pair.exp, out=pair.cols(0, d_id), flags=flags)
@@ -144,10 +147,19 @@ class CouplingTransform(Transform):
             xs = x[r0:r1]
             state = D.run_trunk(chain, xs, None, True, x_pair=pair.cols(0, d_id).rows(r0, r1), flags=flags)
             with K.timed("rq_coupling_final", r1 - r0):
-                self._fused_final(chain, state, xs, (d_id, self.features - d_id), xs, lad[r0:r1], flags, inverse)
+                if pair_only:
+                    self._fused_final(chain, state, xs, (d_id, self.features - d_id), None, lad[r0:r1], flags, inverse,
+                                      y_pair=pair.rows(r0, r1))
+                else:
+                    self._fused_final(chain, state, xs, (d_id, self.features - d_id), xs, lad[r0:r1], flags, inverse)
         if carry is not None:
-            K.split_f16(x[:, d_id:], pair.exp, out=pair.cols(d_id, self.features), flags=flags)
-            carry["pair"] = pair
+            if pair_only:
+                carry["pair"] = pair
+            elif carry.get("pair_only"):          # an affine run follows but the pair-only kernel mode is not in use
+                K.split_f16(x[:, d_id:], pair.exp, out=pair.cols(d_id, self.features), flags=flags)
+                carry["pair"] = pair
+            else:                                 # nobody multiplies this output on the tensor cores
+                carry["pair"] = None
         return x
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None, layout=None, owned=False, carry=None):
@@ -402,9 +414,10 @@ class PiecewiseRationalQuadraticCouplingTransform(PiecewiseCouplingTransform):
         return (config.fuse_coupling and bias is not None and not relu_out and residual is None
                 and K.rq_coupling_final_supported(self.num_bins, self.tails, hidden, hidden))
 
-    def _fused_final(self, chain, state, x, t_cols, out, lad, flags, inverse):
+    def _fused_final(self, chain, state, x, t_cols, out, lad, flags, inverse, y_pair=None):
         weight, bias = chain[-1][0], chain[-1][1]
         m = self._transform_dim_multiplier()
         mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
         wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.num_transform_features, m, mp)
-        K.rq_coupling_final(self._spline_desc(), inverse, state.pair, wp_pair, bias_packed, x, t_cols, out, lad, flags)
+        K.rq_coupling_final(self._spline_desc(), inverse, state.pair, wp_pair, bias_packed, x, t_cols, out, lad, flags,
+                            y_pair=y_pair)
