@@ -6,6 +6,8 @@ kwargs, state_dict keys and exceptions -- with CUDA fp32 inference executed by h
 libnfk_sm100.so (C ABI: include/nfk.h)."""
 __version__ = "0.1.0"
 
+import os as _os
+
 
 class _Config:
     #: read the device flag word after each public call and raise the reference's exceptions
@@ -17,7 +19,7 @@ class _Config:
     fuse_coupling = True
     #: a fused coupling whose output only feeds a folded affine run writes just the fp16 pair of its transformed block
     #: (no fp32 values, no separate split pass)
-    fused_pair_only = False
+    fused_pair_only = _os.environ.get("NFLOWS_B200_PAIR_ONLY", "0") == "1"
     #: power-of-two exponent applied to activations before they are split into fp16 (hi, lo) pairs for the tensor-core
     #: dense layers: |a| * 2^exp must stay below 65000 (an overflow raises kernels.Float16RangeError) and |a| >= 2^-(3+exp)
     #: keeps the full 22-bit precision; 6 covers 2e-3 .. 1000

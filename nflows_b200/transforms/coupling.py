@@ -128,7 +128,8 @@ class CouplingTransform(Transform):
     def _native_packed(self, x, lad, flags, inverse, context, owned, carry=None):
         """Fused path on a tensor already in the [identity | transformed] column order: the conditioner trunk reads the fp16
         pair of the identity block (written by the affine run in front, else split here), the fused kernel overwrites the
-        transformed block in place, and the pair of that block is completed for the affine run behind; nothing is copied."""
+        transformed block in place -- or, when only a folded affine run reads the result, writes just its fp16 pair -- and the
+        pair of the whole row is handed to the affine run behind; nothing is copied."""
         if not owned:
             x = x.clone()
         d_id = self.num_identity_features
@@ -201,7 +202,7 @@ class CouplingTransform(Transform):
                 packed = self._native_packed(K.gather_cols(inputs, layout.cols(inputs.device)), lad, flags, inverse, context,
                                              True)
                 return K.gather_cols(packed, layout.cols(inputs.device, inverse=True), out=outputs)
-            # feature count not a multiple of 4 (no TMA-addressable identity view): gathered trunk input, full copy of the
+            # feature counts not multiples of 8 (no TMA-addressable fp16 identity view): gathered trunk input, full copy of the
             # input as the output, transformed columns overwritten in place
             if self._all_cols is None or self._all_cols.device != inputs.device:
                 self._all_cols = torch.arange(self.features, dtype=torch.int32, device=inputs.device)
