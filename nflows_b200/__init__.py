@@ -18,8 +18,8 @@ class _Config:
     #: run the final conditioner layer and the spline as ONE tensor-core kernel when an instance exists
     fuse_coupling = True
     #: a fused coupling whose output only feeds a folded affine run writes just the fp16 pair of its transformed block
-    #: (no fp32 values, no separate split pass)
-    fused_pair_only = _os.environ.get("NFLOWS_B200_PAIR_ONLY", "0") == "1"
+    #: (no fp32 values, no separate split pass); NFLOWS_B200_PAIR_ONLY=0 switches it off (A/B: 299.6 vs 308.9 ms per cfg-3 step)
+    fused_pair_only = _os.environ.get("NFLOWS_B200_PAIR_ONLY", "1") == "1"
     #: power-of-two exponent applied to activations before they are split into fp16 (hi, lo) pairs for the tensor-core
     #: dense layers: |a| * 2^exp must stay below 65000 (an overflow raises kernels.Float16RangeError) and |a| >= 2^-(3+exp)
     #: keeps the full 22-bit precision; 6 covers 2e-3 .. 1000
