@@ -45,6 +45,9 @@ _SIGNATURES = {
                                  c_int32, c_int32, c_int, c_int, c_int64, c_int32, c_int32, _P, _P]),
     "nfk_absmax": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P]),
     "nfk_split_f16": (c_int, [_P, c_int64, c_int32, c_int, c_int32, _P, _P, c_int64, c_int64, _P, _P]),
+    "nfk_residual_trunk_f16x3_supported": (c_int, [c_int32, c_int32, c_int64, c_int64]),
+    "nfk_residual_trunk_f16x3": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P, c_int64, _P, _P,
+                                         c_int64, c_int64, c_int32, _P, _P]),
     "nfk_rq_coupling_final_supported": (c_int, [c_int32, c_int32, c_int32, c_int64]),
     "nfk_rq_coupling_final_padded_params": (c_int32, [c_int32, c_int32]),
     "nfk_rq_coupling_final_f16x3": (c_int, [POINTER(NfkSplineDesc), c_int, _P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P,
