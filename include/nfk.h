@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NFK_ABI_VERSION 2
+#define NFK_ABI_VERSION 3
 
 #define NFK_OK 0
 #define NFK_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -153,6 +153,45 @@ int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int inverse, const vo
                                const int32_t* t_cols, int32_t t_col0, int32_t d_t, float* y, int64_t ldy, void* y_hi,
                                void* y_lo, int64_t lds, int32_t y_exp, float* lad_accum, int64_t n_rows, int32_t* flags,
                                void* stream);
+
+/* ---- the whole RQ-coupling step in ONE kernel --------------------------------------------------------------------- */
+/* Conditioner (initial layer, square layers of the residual blocks, final layer) + spline + scatter + log|det| of
+ * PiecewiseRationalQuadraticCouplingTransform.forward / inverse (coupling.py:73-99, 105-130, 279-293, 549-582) with a
+ * ResidualNet / MLP conditioner (nn/nets/resnet.py:39-55, 92-100; nn/nets/mlp.py) -- one tcgen05 kernel, no intermediate
+ * tensor in global memory: a CTA keeps the hidden activation of a 128-row tile in shared memory as the fp16 split pair
+ * the next layer multiplies and streams only weights.  Same arithmetic as nfk_linear_f16x3 / nfk_rq_coupling_final_f16x3.
+ *   a_hi/a_lo   : fp16 split pair (exponent a_exp) of the conditioner input [n_rows, in_features] (the identity features,
+ *                 pre-activated if the first layer applies an activation to its input)
+ *   w0_hi/w0_lo : pair (w0_exp) of the initial layer's weight [hidden, in_features]
+ *   wt_hi/wt_lo : pairs of the num_square_layers hidden x hidden weights stacked row-wise, layer l with exponent wt_exps[l]
+ *                 (HOST array); may be NULL when num_square_layers == 0
+ *   bias_trunk  : fp32 [(1 + num_square_layers) * hidden]
+ *   layer_flags : HOST array [1 + num_square_layers], bits as in nfk_residual_trunk_f16x3 (1 relu on the output, 2 add the
+ *                 saved skip tensor, 4 save the fp32 output as the skip tensor, 8 the next layer takes relu of this output)
+ *   act_exp     : exponent of every hidden activation pair
+ *   wp_hi/wp_lo, bias_packed, x, t_cols, t_col0, d_t, y | (y_hi, y_lo, y_exp), lad_accum: as nfk_rq_coupling_final_f16x3
+ *   h_hi/h_lo   : when non-NULL the kernel stops after the last trunk layer and writes that layer's output pair (exponent
+ *                 act_exp, pre-activated per its flag bit 8) here instead of running the final layer + spline
+ *   workspace   : nfk_rq_coupling_step_workspace_bytes(hidden) bytes of device scratch (skip tensors, one tile per CTA) */
+typedef struct NfkCouplingStep {
+    const NfkSplineDesc* spline;
+    int32_t inverse;
+    const void* a_hi; const void* a_lo; int64_t lda; int32_t a_exp; int32_t in_features;
+    const void* w0_hi; const void* w0_lo; int64_t ldw0; int32_t w0_exp;
+    const void* wt_hi; const void* wt_lo; int64_t ldwt; const int32_t* wt_exps;
+    const float* bias_trunk; const int32_t* layer_flags; int32_t num_square_layers; int32_t act_exp;
+    const void* wp_hi; const void* wp_lo; int64_t ldwp; int32_t wp_exp; const float* bias_packed; int32_t hidden_features;
+    const float* x; int64_t ldx; const int32_t* t_cols; int32_t t_col0; int32_t d_t;
+    float* y; int64_t ldy; void* y_hi; void* y_lo; int64_t lds; int32_t y_exp;
+    void* h_hi; void* h_lo; int64_t ldh;
+    float* lad_accum; int64_t n_rows;
+    void* workspace; size_t workspace_bytes;
+    int32_t* flags;
+} NfkCouplingStep;
+int nfk_rq_coupling_step_supported(int32_t num_bins, int32_t linear_tails, int32_t hidden_features, int32_t in_features,
+                                   int32_t num_square_layers);
+size_t nfk_rq_coupling_step_workspace_bytes(int32_t hidden_features);
+int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* step, void* stream);
 
 /* ---- row-wise elementwise transforms -------------------------------------------------------------------- */
 /* out[n, j] = x[n*ldx + cols[j]] (identity_split gather, coupling.py:82; Permutation._permute,

@@ -17,6 +17,9 @@ class _Config:
     param_chunk_mib = 64
     #: run the final conditioner layer and the spline as ONE tensor-core kernel when an instance exists
     fuse_coupling = True
+    #: run conditioner trunk + final layer + spline of an RQ coupling as ONE kernel (nfk_rq_coupling_step_f16x3);
+    #: NFLOWS_B200_STEP_KERNEL=0 falls back to the round-1 launch sequence (one GEMM per trunk layer + fused final layer)
+    coupling_step_kernel = _os.environ.get("NFLOWS_B200_STEP_KERNEL", "1") == "1"
     #: a fused coupling whose output only feeds a folded affine run writes just the fp16 pair of its transformed block
     #: (no fp32 values, no separate split pass); NFLOWS_B200_PAIR_ONLY=0 switches it off (A/B: 299.6 vs 308.9 ms per cfg-3 step)
     fused_pair_only = _os.environ.get("NFLOWS_B200_PAIR_ONLY", "1") == "1"

@@ -6,7 +6,7 @@ is missing or the device is not sm_100, calls raise.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 import torch
 
@@ -28,6 +28,25 @@ class NfkSplineDesc(Structure):
 
 
 _P = c_void_p  # device pointers travel as integers
+
+
+class NfkCouplingStep(Structure):
+    """include/nfk.h: NfkCouplingStep (field for field)."""
+    _fields_ = [
+        ("spline", POINTER(NfkSplineDesc)), ("inverse", c_int32),
+        ("a_hi", _P), ("a_lo", _P), ("lda", c_int64), ("a_exp", c_int32), ("in_features", c_int32),
+        ("w0_hi", _P), ("w0_lo", _P), ("ldw0", c_int64), ("w0_exp", c_int32),
+        ("wt_hi", _P), ("wt_lo", _P), ("ldwt", c_int64), ("wt_exps", POINTER(c_int32)),
+        ("bias_trunk", _P), ("layer_flags", POINTER(c_int32)), ("num_square_layers", c_int32), ("act_exp", c_int32),
+        ("wp_hi", _P), ("wp_lo", _P), ("ldwp", c_int64), ("wp_exp", c_int32), ("bias_packed", _P), ("hidden_features", c_int32),
+        ("x", _P), ("ldx", c_int64), ("t_cols", _P), ("t_col0", c_int32), ("d_t", c_int32),
+        ("y", _P), ("ldy", c_int64), ("y_hi", _P), ("y_lo", _P), ("lds", c_int64), ("y_exp", c_int32),
+        ("h_hi", _P), ("h_lo", _P), ("ldh", c_int64),
+        ("lad_accum", _P), ("n_rows", c_int64),
+        ("workspace", _P), ("workspace_bytes", c_size_t),
+        ("flags", _P),
+    ]
+
 
 _SIGNATURES = {
     "nfk_version": (c_int, []),
@@ -53,6 +72,9 @@ _SIGNATURES = {
     "nfk_rq_coupling_final_f16x3": (c_int, [POINTER(NfkSplineDesc), c_int, _P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P,
                                             c_int32, _P, c_int64, _P, c_int32, c_int32, _P, c_int64, _P, _P, c_int64, c_int32, _P,
                                             c_int64, _P, _P]),
+    "nfk_rq_coupling_step_supported": (c_int, [c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "nfk_rq_coupling_step_workspace_bytes": (c_size_t, [c_int32]),
+    "nfk_rq_coupling_step_f16x3": (c_int, [POINTER(NfkCouplingStep), _P]),
     "nfk_gather_cols": (c_int, [_P, c_int64, _P, c_int32, _P, c_int64, c_int64, _P]),
     "nfk_actnorm": (c_int, [_P, c_int64, _P, _P, _P, c_int64, _P, c_float, c_int64, c_int32, c_int, _P]),
     "nfk_add_const": (c_int, [_P, c_float, c_int64, _P]),
@@ -83,8 +105,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError here means header and library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.nfk_version() != 2:
-        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 2".format(lib.nfk_version()))
+    if lib.nfk_version() != 3:
+        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 3".format(lib.nfk_version()))
     _lib = lib
     return lib
 

@@ -118,6 +118,89 @@ def pack_trunk(body_tail):
     return hit[1]
 
 
+class StepPlan:
+    """Operands of nfk_rq_coupling_step_f16x3 for every layer of a conditioner but the last: Pair16 of the initial layer's weight,
+    stacked pairs + exponents of the square layers, stacked biases, layer flags."""
+
+    def __init__(self, body):
+        import ctypes
+        h = body[0][0].shape[0]
+        dev = body[0][0].device
+        self.hidden = h
+        self.act_exp = act_exp()
+        w0 = body[0][0].detach().contiguous()
+        self.w0 = K.split_f16(w0, K.weight_exp(w0))
+        tail = body[1:]
+        self.wt_hi = self.wt_lo = None
+        exps = []
+        if tail:
+            self.wt_hi = torch.empty(len(tail) * h, h, dtype=torch.float16, device=dev)
+            self.wt_lo = torch.empty_like(self.wt_hi)
+            for l, layer in enumerate(tail):
+                w = layer[0].detach().contiguous()
+                e = K.weight_exp(w)
+                K.split_f16(w, e, out=K.Pair16(self.wt_hi[l * h:(l + 1) * h], self.wt_lo[l * h:(l + 1) * h], e))
+                exps.append(e)
+        self.wt_exps_c = (ctypes.c_int32 * max(1, len(exps)))(*exps)
+        self.bias = torch.cat([layer[1].detach().reshape(-1).float() for layer in body]).contiguous()
+        self.layer_flags = None
+        self.layer_flags_c = None
+
+    def set_flags(self, flags):
+        import ctypes
+        self.layer_flags = list(flags)
+        self.layer_flags_c = (ctypes.c_int32 * len(flags))(*[int(f) for f in flags])
+        return self
+
+
+_STEP_CACHE = {}
+
+
+def plan_step_kernel(chain):
+    """Layer flags of nfk_rq_coupling_step_f16x3 for chain[:-1] (initial layer + square hidden layers), or None when the chain
+    does not have that shape: one hidden width (a multiple of 32, <= 256), biases everywhere, skip adds that take the output
+    of the layer two before (ResidualNet blocks), no relu on the first layer's input or between a skip add and its accumulate."""
+    body = chain[:-1]
+    if not body or chain[0][2]:
+        return None
+    h = body[0][0].shape[0]
+    flags = []
+    saved = None                                     # index of the layer whose fp32 output is the saved skip tensor
+    for i, (weight, bias, relu_in, relu_out, residual) in enumerate(body):
+        if bias is None or weight.shape[0] != h or (i > 0 and weight.shape[1] != h):
+            return None
+        f = 1 if relu_out else 0
+        if residual == "skip":
+            if relu_out or saved is None or saved != i - 2:
+                return None
+            f |= 2
+        elif residual is not None:
+            return None
+        if i + 2 < len(chain) and chain[i + 2][4] == "skip":
+            f |= 4
+            saved = i
+        if chain[i + 1][2]:
+            f |= 8
+        flags.append(f)
+    return flags
+
+
+def step_plan(chain):
+    """Cached StepPlan of a chain (rebuilt when any trunk parameter changes)."""
+    body = chain[:-1]
+    key = tuple(id(layer[0]) for layer in body)
+    sig = tuple((layer[0].data_ptr(), layer[0]._version, layer[1].data_ptr(), layer[1]._version, str(layer[0].device))
+                for layer in body) + (act_exp(),)
+    hit = _STEP_CACHE.get(key)
+    if hit is None or hit[0] != sig:
+        flags = plan_step_kernel(chain)
+        hit = (sig, StepPlan(body).set_flags(flags), [layer[0] for layer in body])
+        _STEP_CACHE[key] = hit
+        if len(_STEP_CACHE) > 256:
+            _STEP_CACHE.pop(next(iter(_STEP_CACHE)))
+    return hit[1]
+
+
 class ChainState:
     """Activation between two layers: fp32 tensor (`raw`, FFMA path) or the Pair16 a tensor-core layer consumes."""
 

@@ -289,3 +289,73 @@ def rq_coupling_final(desc, inverse, a, wp, bias_packed, x, t_cols, y, lad_accum
         y_pair.lo.data_ptr() if y_pair is not None else 0, y_pair.hi.stride(0) if y_pair is not None else 0,
         y_pair.exp if y_pair is not None else 0, N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
     return y
+
+
+# ---- the whole RQ-coupling step in one kernel --------------------------------------------------------------------------
+def rq_coupling_step_supported(num_bins, tails, hidden, in_features, num_square_layers):
+    return bool(N.load().nfk_rq_coupling_step_supported(int(num_bins), 1 if tails == "linear" else 0, int(hidden), int(in_features),
+                                                        int(num_square_layers)))
+
+
+_STEP_WORKSPACE = {}
+
+
+def step_workspace(device, hidden):
+    """Scratch of the coupling-step kernel (skip tensors, one 128 x hidden tile per CTA), one buffer per (device, stream)."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream, int(hidden))
+    ws = _STEP_WORKSPACE.get(key)
+    if ws is None:
+        nbytes = int(N.lib().nfk_rq_coupling_step_workspace_bytes(int(hidden)))
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        _STEP_WORKSPACE[key] = ws
+    return ws
+
+
+def rq_coupling_step(plan, a, desc=None, inverse=False, wp=None, bias_packed=None, x=None, t_cols=None, y=None, lad_accum=None,
+                     flags=None, y_pair=None, h_pair=None):
+    """ONE launch for conditioner + spline of an RQ coupling (include/nfk.h: nfk_rq_coupling_step_f16x3).
+    plan: dense.StepPlan (packed trunk weights, layer flags); a: Pair16 of the conditioner input.
+    Either (desc, wp, bias_packed, x, t_cols, y | y_pair, lad_accum) for the full step, or h_pair (Pair16 [n, hidden]) to stop after
+    the trunk and get its output pair."""
+    n, k0 = a.shape
+    h = plan.hidden
+    ws = step_workspace(a.hi.device, h)
+    d = N.NfkCouplingStep()
+    d.spline = ctypes.pointer(desc) if desc is not None else None
+    d.inverse = int(inverse)
+    d.a_hi, d.a_lo, d.lda, d.a_exp, d.in_features = a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, k0
+    d.w0_hi, d.w0_lo, d.ldw0, d.w0_exp = plan.w0.hi.data_ptr(), plan.w0.lo.data_ptr(), plan.w0.hi.stride(0), plan.w0.exp
+    nsq = len(plan.layer_flags) - 1
+    if nsq:
+        d.wt_hi, d.wt_lo, d.ldwt = plan.wt_hi.data_ptr(), plan.wt_lo.data_ptr(), plan.wt_hi.stride(0)
+        d.wt_exps = plan.wt_exps_c
+    d.bias_trunk = plan.bias.data_ptr()
+    d.layer_flags = plan.layer_flags_c
+    d.num_square_layers = nsq
+    d.act_exp = plan.act_exp
+    d.hidden_features = h
+    d.n_rows = n
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    d.flags = N.ptr(flags)
+    if h_pair is not None:
+        if h_pair.exp != plan.act_exp:
+            raise ValueError("trunk output pair must carry the plan's activation exponent")
+        d.h_hi, d.h_lo, d.ldh = h_pair.hi.data_ptr(), h_pair.lo.data_ptr(), h_pair.hi.stride(0)
+        tag = "trunk_step_%dx%d" % (h, nsq + 1)
+    else:
+        if isinstance(t_cols, tuple):
+            d.t_cols, d.t_col0, d.d_t = None, int(t_cols[0]), int(t_cols[1])
+        else:
+            d.t_cols, d.t_col0, d.d_t = t_cols.data_ptr(), -1, t_cols.numel()
+        d.wp_hi, d.wp_lo, d.ldwp, d.wp_exp = wp.hi.data_ptr(), wp.lo.data_ptr(), wp.hi.stride(0), wp.exp
+        d.bias_packed = bias_packed.data_ptr()
+        d.x, d.ldx = x.data_ptr(), x.stride(0)
+        if y is not None:
+            d.y, d.ldy = y.data_ptr(), y.stride(0)
+        if y_pair is not None:
+            d.y_hi, d.y_lo, d.lds, d.y_exp = y_pair.hi.data_ptr(), y_pair.lo.data_ptr(), y_pair.hi.stride(0), y_pair.exp
+        d.lad_accum = N.ptr(lad_accum)
+        tag = "rq_coupling_step"
+    with timed(tag, n):
+        N.check(N.lib().nfk_rq_coupling_step_f16x3(ctypes.byref(d), N.stream()))
+    return y if y is not None else (y_pair if y_pair is not None else h_pair)

@@ -143,9 +143,16 @@ class CouplingTransform(Transform):
             pair = K.Pair16.empty(n, self.features, D.act_exp(), x.device)
             K.split_f16(x[:, :d_id], pair.exp, out=pair.cols(0, d_id), flags=flags)
         block = max(128, int(config.coupling_block_rows))
+        use_step = self._step_ready(chain)
         for r0 in range(0, n, block):
             r1 = min(n, r0 + block)
             xs = x[r0:r1]
+            if use_step:
+                # conditioner + spline of this row block in ONE launch (nfk_rq_coupling_step_f16x3)
+                self._fused_step(chain, pair.cols(0, d_id).rows(r0, r1), xs, (d_id, self.features - d_id),
+                                 None if pair_only else xs, lad[r0:r1], flags, inverse,
+                                 y_pair=pair.rows(r0, r1) if pair_only else None)
+                continue
             state = D.run_trunk(chain, xs, None, True, x_pair=pair.cols(0, d_id).rows(r0, r1), flags=flags)
             with K.timed("rq_coupling_final", r1 - r0):
                 if pair_only:
@@ -243,6 +250,9 @@ class CouplingTransform(Transform):
         raise NotImplementedError()
 
     def _fused_final_ready(self, chain):
+        return False
+
+    def _step_ready(self, chain):
         return False
 
     # ---- subclass API (same names as the reference) -------------------------------------------------------
@@ -422,3 +432,20 @@ class PiecewiseRationalQuadraticCouplingTransform(PiecewiseCouplingTransform):
         wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.num_transform_features, m, mp)
         K.rq_coupling_final(self._spline_desc(), inverse, state.pair, wp_pair, bias_packed, x, t_cols, out, lad, flags,
                             y_pair=y_pair)
+
+    def _step_ready(self, chain):
+        """The whole step (conditioner trunk + final layer + spline) runs as one kernel."""
+        if not (config.coupling_step_kernel and self._fused_final_ready(chain)):
+            return False
+        if D.plan_step_kernel(chain) is None:
+            return False
+        hidden = chain[-1][0].shape[1]
+        return K.rq_coupling_step_supported(self.num_bins, self.tails, hidden, chain[0][0].shape[1], len(chain) - 2)
+
+    def _fused_step(self, chain, a_pair, x, t_cols, out, lad, flags, inverse, y_pair=None):
+        weight, bias = chain[-1][0], chain[-1][1]
+        m = self._transform_dim_multiplier()
+        mp = K.rq_coupling_final_padded_params(self.num_bins, self.tails)
+        wp_pair, bias_packed = D.pack_final_spline(weight, bias, self.num_transform_features, m, mp)
+        K.rq_coupling_step(D.step_plan(chain), a_pair, self._spline_desc(), inverse, wp_pair, bias_packed, x, t_cols, out, lad,
+                           flags, y_pair=y_pair)
