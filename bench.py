@@ -1,17 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the BASELINE.json metric: Flow.log_prob samples/s on the 10-layer RQ-NSF, D=784, batch 2^20.
+"""Benchmark of the BASELINE.json metric: Flow.log_prob samples/s on the 10-layer RQ-NSF, D=784, batch 2^20, sharded over N GPUs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--rows R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--rows R] [--weak]
 
-One "step" = one Flow.log_prob pass over one synthetic Gaussian batch of R rows per GPU (weak scaling: every rank
-owns R rows and a replica of the weights; the only collective is the all-gather of per-sample log-probs).  Prints
-ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for what each key means.
+One "step" = one Flow.log_prob pass over ONE synthetic Gaussian batch of R rows (default 2^20, BASELINE.json configs[2]).
+With N GPUs (torchrun, one rank per GPU) the batch is SHARDED: every rank owns R/N rows and a replica of the weights
+(strong scaling); the only collective is the all-gather of the per-sample log-probs.  `--weak`
+gives every rank R rows instead (the round-1 measurement).  Prints ONE JSON line (rank 0).  DESIGN.md section 6 explains
+every key.
 """
 import os
 os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 import argparse
 import json
-import os
 import subprocess
 import sys
 import threading
@@ -25,15 +26,18 @@ if ROOT not in sys.path:
 
 FEATURES, HIDDEN, LAYERS, BINS, BLOCKS = 784, 256, 10, 8, 2
 METRIC = "Flow.log_prob samples/sec, 10-layer RQ-NSF D=784"
+WORKLOAD = "cfg3 10x[ActNorm,RandPerm+LULinear,RQ-coupling(H=256,2 blocks,K=8,B=3)] D=784 log_prob"
 # algorithmic work per sample
 D_ID = FEATURES // 2
 M_PARAMS = 3 * BINS - 1
-FLOP_FINAL_PER_ROW = 2 * HIDDEN * (D_ID * M_PARAMS)                      # final conditioner layer, one coupling
-FLOP_PER_SAMPLE = LAYERS * (2 * (D_ID * HIDDEN + 2 * BLOCKS * HIDDEN * HIDDEN + HIDDEN * D_ID * M_PARAMS)
-                            + 2 * FEATURES * FEATURES)
-
-
-#: MMA columns issued per useful parameter column in the fused kernel at cfg 3: 24/23 rows per feature, 400/392 features
+FLOP_COND_PER_ROW = 2 * (D_ID * HIDDEN + 2 * BLOCKS * HIDDEN * HIDDEN + HIDDEN * D_ID * M_PARAMS)   # one coupling's conditioner
+FLOP_FINAL_PER_ROW = 2 * HIDDEN * (D_ID * M_PARAMS)                                                 # ... its final layer alone
+FLOP_AFFINE_PER_ROW = 2 * FEATURES * FEATURES
+FLOP_PER_SAMPLE = LAYERS * (FLOP_COND_PER_ROW + FLOP_AFFINE_PER_ROW)
+#: MMA flops the coupling-step kernel executes per row: 3 fp16 MMAs per product; K = 392 padded to 13 slabs of 32; 24 packed
+#: rows per 23-parameter feature
+MMA_EXEC_STEP_PER_ROW = 3 * 2 * (416 * HIDDEN + 2 * BLOCKS * HIDDEN * HIDDEN + HIDDEN * D_ID * 24)
+#: round-1 launch sequence (NFLOWS_B200_STEP_KERNEL=0): final layer in 240-column tiles, 24/23 rows per feature, 400/392 features
 FUSED_PAD = (24.0 / 23.0) * (400.0 / 392.0)
 
 
@@ -91,6 +95,14 @@ def build_flow(seed=0):
     return recipes.perturb_(recipes.rq_nsf(FEATURES, HIDDEN, LAYERS, num_bins=BINS, tail_bound=3.0, num_blocks=BLOCKS).eval())
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line -- the SAME keys for the native and the reference arm."""
+    rows = args.rows if args.weak else args.rows // world
+    return {"workload": WORKLOAD, "global_batch": rows * world, "rows_per_gpu": rows,
+            "parallelism": "dp%d batch-shard, %s" % (world, "weak: %d rows per GPU" % rows if args.weak else "one 2^20-row batch sharded"),
+            "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (rows * FEATURES * 4 / 1e9)}
+
+
 def cpu_oracle_rate(flow, budget_s=12.0, chunk=2048, max_rows=1 << 15):
     """The CPU restatement of the reference path (oracle/, torch ATen fp32, all host threads) on a bounded sample."""
     from oracle import flow_oracle as O
@@ -108,29 +120,42 @@ def cpu_oracle_rate(flow, budget_s=12.0, chunk=2048, max_rows=1 << 15):
     return rows / dt, rows, torch.get_num_threads()
 
 
-def torch_cuda_rate(flow, dev, budget_s=6.0, chunk=1 << 14, max_rows=1 << 18):
-    """SURVEY.md section 8(d) "reference-CUDA baseline": the same restatement of the reference path (oracle/, plain torch ops,
-    true-fp32 matmuls) with weights and data on the GPU, chunked so the [chunk, d_t * 23] parameter tensor the reference
-    materialises fits.  A reported context figure, like cpu_baseline; none of this package's kernels run here."""
+def torch_cuda_rate(flow, dev, budget_s=3.0, chunks=(1 << 14, 1 << 15, 1 << 16, 1 << 17)):
+    """SURVEY.md section 8(d) "reference-CUDA baseline": the restatement of the reference path (oracle/, plain torch ops, true-fp32
+    matmuls) with weights and data on the GPU, looped over chunks so the [chunk, d_t * 23] parameter tensor the reference
+    materialises fits; the chunk size is swept and the best rate reported.  A context figure like cpu_baseline; none of this
+    package's kernels run here."""
     from oracle import flow_oracle as O
     torch.backends.cuda.matmul.allow_tf32 = False
     sd = {k: v.detach().to(dev).clone() for k, v in flow.state_dict().items()}
     spec = O.nsf_spec(LAYERS, num_bins=BINS, tail_bound=3.0)
     g = torch.Generator(device=dev).manual_seed(123)
-    x = torch.randn(chunk, FEATURES, device=dev, generator=g)
-    with torch.no_grad():
-        O.flow_log_prob(sd, spec, x[:1024])
-        torch.cuda.synchronize()
-        rows, t0 = 0, time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        while rows < max_rows and time.perf_counter() - t0 < budget_s:
-            O.flow_log_prob(sd, spec, x)
-            rows += chunk
-            torch.cuda.synchronize()
-        e1.record()
-        torch.cuda.synchronize()
-    return rows / (e0.elapsed_time(e1) * 1e-3), rows
+    best, tried = None, {}
+    for chunk in chunks:
+        try:
+            x = torch.randn(chunk, FEATURES, device=dev, generator=g)
+            with torch.no_grad():
+                O.flow_log_prob(sd, spec, x)
+                torch.cuda.synchronize()
+                rows, t0 = 0, time.perf_counter()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                while rows < (1 << 19) and time.perf_counter() - t0 < budget_s:
+                    O.flow_log_prob(sd, spec, x)
+                    rows += chunk
+                    torch.cuda.synchronize()
+                e1.record()
+                torch.cuda.synchronize()
+            rate = rows / (e0.elapsed_time(e1) * 1e-3)
+            tried[str(chunk)] = round(rate, 1)
+            if best is None or rate > best[0]:
+                best = (rate, chunk, rows)
+            del x
+        except RuntimeError as exc:           # out of memory at this chunk size: keep what fitted
+            tried[str(chunk)] = "failed: %s" % str(exc).split("\n")[0][:80]
+            torch.cuda.empty_cache()
+            break
+    return best, tried
 
 
 def spline_hbm_roofline(dev, peaks, rows=1 << 20, d_t=32, bins=8, iters=10):
@@ -165,11 +190,67 @@ def spline_hbm_roofline(dev, peaks, rows=1 << 20, d_t=32, bins=8, iters=10):
             "workload": "rows=2^20 d_t=32 K=8 params in HBM (3.2 GB > L2)", "peak_kind": "copy bandwidth, %s" % peaks["source"]}
 
 
+def extra_workloads(dev, flow):
+    """The other single-GPU configurations of BASELINE.json, one short timing each (CUDA events, 3 warm-ups): cfg 2 (single RQ
+    coupling D=64 forward + inverse at 2^20 rows), Flow.sample of the cfg-3 flow, cfg 4 (autoregressive RQ inverse, 2^18 x 64)."""
+    from nflows_b200 import transforms as T
+    from nflows_b200.flows import recipes
+    out = {}
+
+    def timed(fn, iters=5, warm=3):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    with torch.no_grad():
+        try:
+            torch.manual_seed(0)
+            layer = recipes.rq_coupling_layer(64, 128).eval().to(dev)
+            x = torch.randn(1 << 20, 64, device=dev)
+            y, _ = layer(x)
+            ms_f = timed(lambda: layer(x))
+            ms_i = timed(lambda: layer.inverse(y))
+            out["cfg2_rq_coupling_D64_2^20"] = {"forward_ms": ms_f, "inverse_ms": ms_i,
+                                                "forward_samples_per_s": (1 << 20) / (ms_f * 1e-3),
+                                                "inverse_samples_per_s": (1 << 20) / (ms_i * 1e-3)}
+            del x, y, layer
+        except Exception as exc:
+            out["cfg2_rq_coupling_D64_2^20"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+        try:
+            n = 1 << 18
+            ms = timed(lambda: flow.sample(n), iters=3, warm=2)
+            out["cfg3_sample_2^18"] = {"ms": ms, "samples_per_s": n / (ms * 1e-3)}
+        except Exception as exc:
+            out["cfg3_sample_2^18"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+        try:
+            torch.manual_seed(0)
+            ar = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=64, hidden_features=256, num_bins=8, tails="linear",
+                                                                            tail_bound=3.0, num_blocks=2).eval().to(dev)
+            z = torch.randn(1 << 18, 64, device=dev)
+            ms = timed(lambda: ar.inverse(z), iters=2, warm=1)
+            ms_f = timed(lambda: ar(z), iters=3, warm=2)
+            out["cfg4_ar_rq_D64_2^18"] = {"inverse_ms": ms, "inverse_samples_per_s": (1 << 18) / (ms * 1e-3), "forward_ms": ms_f,
+                                          "forward_samples_per_s": (1 << 18) / (ms_f * 1e-3)}
+        except Exception as exc:
+            out["cfg4_ar_rq_D64_2^18"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference itself cannot travel to the GPU box)."""
+    """--impl reference: the reference's CPU path (oracle port; the Python reference itself cannot travel to the GPU box), on
+    ALL host threads -- torchrun exports OMP_NUM_THREADS=1, undone here; ranks other than 0 exit without work."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     flow = build_flow()
     rates, rows_total = [], 0
     for i in range(args.warmup + args.steps):
@@ -180,11 +261,10 @@ def run_reference(args):
     value = sum(rates) / len(rates)
     sample = "{} rows per step in chunks of 2048 (of the {}-row workload)".format(rows_total // max(1, args.steps), args.rows)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * (rows_total / max(1, args.steps)) / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg3 10x[ActNorm,RandPerm+LULinear,RQ-coupling(H=256,2 blocks,K=8,B=3)] D=784 log_prob",
-                   "rows_per_gpu": args.rows},
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -206,7 +286,7 @@ def run_native(args):
     peaks = load_peaks()
 
     flow = build_flow().to(dev)
-    rows = args.rows
+    rows = args.rows if args.weak else args.rows // world          # rows this rank owns
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
     x = torch.randn(rows, FEATURES, device=dev, generator=gen)
     gathered = torch.empty(world * rows, device=dev) if world > 1 else None
@@ -246,17 +326,19 @@ def run_native(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms_total = float(ms.item())
+        lp_local = out[rank * rows:(rank + 1) * rows].clone() if world > 1 else out.clone()
 
         # ---- end to end: pinned host inputs -> H2D -> log_prob -> D2H of the result, every step ------------------
         host_x = torch.empty(rows, FEATURES, pin_memory=True)
         host_x.copy_(x)
         host_out = torch.empty(out.numel(), pin_memory=True)
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = args.steps
+        from nflows_b200 import sharding
+        lp_dev = torch.empty(rows, device=dev)
+        sharding.log_prob_streamed(flow, host_x, dev, chunk_rows=args.e2e_chunk, out=lp_dev)       # warm-up (pinned staging, streams)
         fence()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        from nflows_b200 import sharding
-        lp_dev = torch.empty(rows, device=dev)
         for _ in range(e2e_steps):
             sharding.log_prob_streamed(flow, host_x, dev, chunk_rows=args.e2e_chunk, out=lp_dev)   # H2D overlapped with the kernels
             if world > 1:
@@ -278,21 +360,35 @@ def run_native(args):
 
     ms_per_step = ms_total / args.steps
     value = world * rows / (ms_per_step * 1e-3)
+    config = workload_config(args, world)
+    config.update({"peaks": peaks["source"],
+                   "arithmetic": "fp32 in / fp32 out; dense layers multiply fp16 (hi,lo) split pairs with 3 tcgen05 kind::f16 "
+                                 "MMAs per product (22-bit operands) and accumulate in fp32"})
     result = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": "cfg3 10x[ActNorm,RandPerm+LULinear,RQ-coupling(H=256,2 blocks,K=8,B=3)] D=784 log_prob",
-                   "rows_per_gpu": rows, "global_batch": world * rows, "parallelism": "dp%d batch-shard" % world,
-                   "l2": "inputs (3.3 GB/GPU) exceed the 126 MB L2; no flush needed", "peaks": peaks["source"],
-                   "arithmetic": "fp32 in / fp32 out; dense layers multiply fp16 (hi,lo) split pairs with 3 tcgen05 kind::f16 "
-                                 "MMAs per product (22-bit operands) and accumulate in fp32"},
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": world * rows / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": rows * FEATURES * 4,
-                "d2h_bytes_per_step": int(out.numel()) * 4, "ms_per_step": e2e_ms},
+                "d2h_bytes_per_step": int(out.numel()) * 4, "ms_per_step": e2e_ms, "steps": e2e_steps},
         "tflops_effective": FLOP_PER_SAMPLE * value / 1e12,
     }
-    # ---- roofline of the dominant kernel (final conditioner layer + spline), timed live with CUDA events -----------
+    # ---- parity of the timed result: random rows of the batch just timed against the CPU oracle -----------------------------
+    if not args.no_parity_check:
+        from oracle import flow_oracle as O
+        g = torch.Generator().manual_seed(11)
+        idx = torch.randperm(rows, generator=g)[:args.parity_rows].sort().values
+        xs = x[idx.to(dev)].cpu()
+        sd = {k: v.detach().cpu().clone() for k, v in flow.state_dict().items()}
+        with torch.no_grad():
+            want = O.flow_log_prob(sd, O.nsf_spec(LAYERS, num_bins=BINS, tail_bound=3.0), xs)
+        got = lp_local[idx.to(dev)].cpu()
+        finite = bool(torch.isfinite(lp_local).all().item())
+        rel = float(((got - want).abs() / torch.maximum(torch.maximum(got.abs(), want.abs()), torch.ones_like(want))).max())
+        result["parity_check"] = {"rows": int(idx.numel()), "of_rows": rows, "rel_err": rel, "tolerance": 1e-5, "all_finite": finite,
+                                  "against": "oracle/flow_oracle.py (CPU fp32 restatement of the reference, pinned to reference goldens)",
+                                  "ok": bool(finite and rel <= 1e-5)}
+    # ---- roofline of the dominant kernel, timed live with CUDA events -------------------------------------------------------
     if timeline:
         torch.cuda.synchronize()
         tags = {}
@@ -304,38 +400,51 @@ def run_native(args):
         result["timeline_ms_per_step"] = {k: round(v[0] / args.steps, 3) for k, v in sorted(tags.items(), key=lambda kv: -kv[1][0])}
         top = max(tags.items(), key=lambda kv: kv[1][0])
         tag, (tms, count, rows_k) = top
-        flops = FLOP_FINAL_PER_ROW * rows_k
-        achieved = flops / (tms * 1e-3) / 1e12
+        per_row = {"rq_coupling_step": FLOP_COND_PER_ROW, "rq_coupling_final": FLOP_FINAL_PER_ROW}.get(tag, FLOP_AFFINE_PER_ROW)
+        exec_per_row = {"rq_coupling_step": MMA_EXEC_STEP_PER_ROW, "rq_coupling_final": 3.0 * FLOP_FINAL_PER_ROW * FUSED_PAD}.get(
+            tag, 3.0 * 2 * 800 * 832)
+        achieved = per_row * rows_k / (tms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             t = json.load(open(tpath))
+            t = t.get(tag, t) if isinstance(t.get(tag, None), dict) else t
             if t.get("kernel") == tag and "dram_bytes_per_row" in t:
                 traffic = t["dram_bytes_per_row"] * (rows_k // count)     # per launch, like `achieved`
         result["roofline"] = {"kernel": tag, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                               "frac": achieved / peak, "traffic": traffic, "launches": count,
                               "avg_launch_ms": tms / count, "share_of_step": tms / ms_total,
                               "peak_kind": "bf16 dense sustained, %s" % peaks["source"],
-                              "mma_tflops_executed": 3.0 * achieved * FUSED_PAD,
+                              "mma_tflops_executed": exec_per_row * rows_k / (tms * 1e-3) / 1e12,
+                              "algorithmic_flop_per_row": per_row,
                               "note": "achieved counts ALGORITHMIC flops (2 per weight per row); the kernel executes 3 "
                                       "fp16 MMAs per algorithmic multiply-add plus tile padding (mma_tflops_executed)"}
+        result["roofline_step"] = {"bound": "tensor", "achieved": FLOP_PER_SAMPLE * value / world / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                   "frac": FLOP_PER_SAMPLE * value / world / 1e12 / peak, "what": "whole log_prob step, algorithmic flops, per GPU"}
     if not args.no_spline_roofline:
         result["roofline_spline"] = spline_hbm_roofline(dev, peaks)
+    if world == 1 and not args.no_extras:
+        result["extra"] = extra_workloads(dev, flow)
     # ---- CPU baseline (oracle port) on this box's host cores ---------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
         try:
-            rate, sample_rows = torch_cuda_rate(flow, dev)
-            result["torch_cuda_baseline"] = {"value": rate, "unit": "samples/s", "kind": "port", "sample":
-                                             "%d rows in chunks of 16384, torch eager fp32 (allow_tf32 off) on the same GPU" % sample_rows}
+            best, tried = torch_cuda_rate(flow, dev)
+            result["torch_cuda_baseline"] = {"value": best[0], "unit": "samples/s", "kind": "port", "chunk_rows": best[1],
+                                             "chunk_sweep_samples_per_s": tried,
+                                             "sample": "%d rows in chunks of %d (best of the sweep), torch eager fp32 (allow_tf32 off) on "
+                                                       "the same GPU" % (best[2], best[1])}
         except Exception as exc:     # a context figure only: never let it take the bench line down
             result["torch_cuda_baseline"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
         rate, sample_rows, threads = cpu_oracle_rate(flow.cpu(), budget_s=args.ref_budget, max_rows=args.ref_rows)
         result["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                                   "sample": "%d rows of the same workload in chunks of 2048" % sample_rows}
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+    if "parity_check" in result and not result["parity_check"]["ok"]:
+        sys.exit("parity check failed: %r" % (result["parity_check"],))
 
 
 def main():
@@ -344,10 +453,14 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--rows", type=int, default=1 << 20, help="rows per GPU (BASELINE: 2^20)")
+    ap.add_argument("--rows", type=int, default=1 << 20, help="rows of the batch (BASELINE: 2^20), sharded over the GPUs")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: every GPU owns --rows rows")
     ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per reference step")
     ap.add_argument("--ref-rows", type=int, default=1 << 15)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--parity-rows", type=int, default=512)
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--block-rows", type=int, default=0, help="override config.{trunk,affine,coupling}_block_rows (experiments)")
     ap.add_argument("--no-spline-roofline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=1 << 17, help="rows per host->device chunk of the end-to-end leg")

@@ -38,4 +38,16 @@ class _Config:
     coupling_block_rows = 1 << 19
 
 
+    #: bumped by invalidate_native_caches(); part of every derived-weight cache signature
+    cache_epoch = 0
+
+
 config = _Config()
+
+
+def invalidate_native_caches():
+    """Drop every derived-weight cache (folded ActNorm/Permutation/LU operands, fp16 split pairs, packed final layers, masked
+    MADE weights).  The caches are validated by (data_ptr, tensor version): writes through `param.data` (EMA swaps, old-style
+    optimisers) do not bump the version counter, so call this after such writes -- `module.train()` / `.eval()` on any
+    transform does it for you."""
+    config.cache_epoch += 1

@@ -111,18 +111,18 @@ def load():
     return lib
 
 
-_device_checked = False
+_devices_checked = set()
 
 
 def lib():
-    """The library, after checking once that the current CUDA device can run it."""
-    global _device_checked
+    """The library, after checking once per device that the CURRENT CUDA device can run it."""
     l = load()
-    if not _device_checked:
-        if not torch.cuda.is_available():
-            raise NativeUnavailable("nflows_b200 native kernels need a CUDA device (B200, sm_100a)")
+    if not torch.cuda.is_available():
+        raise NativeUnavailable("nflows_b200 native kernels need a CUDA device (B200, sm_100a)")
+    dev = torch.cuda.current_device()
+    if dev not in _devices_checked:
         check(l.nfk_check_device(), l)
-        _device_checked = True
+        _devices_checked.add(dev)
     return l
 
 

@@ -22,6 +22,18 @@ inline int check_launch(const char* what) {
     return NFK_OK;
 }
 
+// Latch for one-time PER-DEVICE setup (cudaFuncSetAttribute and the like): a process may run flows on several GPUs.
+struct DeviceOnce {
+    std::atomic<uint64_t> done{0};
+    bool pending(int* dev) {
+        int d = 0;
+        cudaGetDevice(&d);
+        *dev = d;
+        return ((done.load(std::memory_order_acquire) >> (d & 63)) & 1ull) == 0;
+    }
+    void mark(int dev) { done.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace nfk

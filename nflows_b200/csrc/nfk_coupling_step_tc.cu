@@ -48,11 +48,12 @@ constexpr int STEP_G2_LO_OFF = 12288;
 constexpr int STEP_BN_MAX = 192;                                     // widest final-layer column tile
 constexpr int STEP_NBAR = 5;                                         // ring barriers (max stages of any geometry)
 constexpr int STEP_BAR_OFF = STEP_R_BYTES + STEP_RING_BYTES;
-constexpr int STEP_LAD_OFF = STEP_BAR_OFF + 256;                     // [128] fp32 partial log|det| of warpgroup 1
-constexpr int STEP_BIAS_OFF = STEP_LAD_OFF + 512;                    // [2][256] fp32 packed bias of the current / next column tile
-constexpr int STEP_Y_OFF = STEP_BIAS_OFF + 2048 + 256;               // 3 x 4 KB output staging (128-byte aligned)
+constexpr int STEP_BIAS_OFF = STEP_BAR_OFF + 256;                    // [2][192] fp32 packed bias of the current / next column tile
+constexpr int STEP_Y_OFF = STEP_BIAS_OFF + 2 * STEP_BN_MAX * 4;      // 3 x 4 KB output staging (128-byte aligned)
 constexpr int STEP_Y_BUF_BYTES = 4096;
-constexpr int STEP_SMEM_BYTES = STEP_Y_OFF + 3 * STEP_Y_BUF_BYTES + 1024 /*alignment slack*/;
+constexpr int STEP_X_OFF = STEP_Y_OFF + 3 * STEP_Y_BUF_BYTES;        // 4 KB: every epilogue thread's next inputs (cp.async), and
+constexpr int STEP_X_BYTES = 4096;                                   // at the end of a row block the log|det| partials
+constexpr int STEP_SMEM_BYTES = STEP_X_OFF + STEP_X_BYTES + 1024 /*alignment slack*/;
 static_assert(STEP_G0_STAGES * STAGE_BYTES <= STEP_R_BYTES + STEP_RING_BYTES, "G0 ring");
 static_assert(STEP_G1_UNITS * STEP_G1_UNIT_BYTES <= STEP_RING_BYTES && STEP_G2_STAGES * STEP_G2_STAGE_BYTES <= STEP_RING_BYTES, "ring");
 static_assert(STEP_Y_OFF % 128 == 0, "staging alignment");
@@ -64,21 +65,25 @@ constexpr int SL_ADD_SKIP = 2;     // + the saved skip tensor (never combined wi
 constexpr int SL_SAVE_SKIP = 4;    // the fp32 result is the skip tensor of a later layer
 constexpr int SL_SPLIT_RELU = 8;   // the consumer of this layer's output applies relu to its input
 
-// Column tile of the final layer: EWG = 2 epilogue warpgroups, FPT features per thread (4, 2 or 1), MP packed rows per feature
-template <int NB, bool TAILS>
+// Column tile of the final layer: TF features (8, 4 or 2) of MP packed rows each, shared by EWG epilogue warpgroups (FPT
+// features per thread).  EWG = 4 puts four warps on every scheduler: the spline epilogue is a long dependent instruction
+// stream, two warps per scheduler left 56 % of the issue slots empty (ncu, r2: issue active 44 %, tensor pipe 43 %).
+template <int NB, bool TAILS, int EWG = 2>
 struct StepCfg {
     static constexpr int M = TAILS ? 3 * NB - 1 : 3 * NB + 1;
     static constexpr int MP = (M + 7) / 8 * 8;
-    static constexpr int FPT = 2 * 4 * MP <= STEP_BN_MAX ? 4 : (2 * 2 * MP <= STEP_BN_MAX ? 2 : 1);
+    static constexpr int TF = 8 * MP <= STEP_BN_MAX ? 8 : (4 * MP <= STEP_BN_MAX ? 4 : 2);   // features per column tile
+    static constexpr int FPT = TF / EWG;                 // features per epilogue thread
     static constexpr int HC = FPT * MP;                  // accumulator columns per epilogue thread
-    static constexpr int TF = 2 * FPT;                   // features per column tile: 8, 4 or 2
-    static constexpr int BN = 2 * HC;                    // MMA N = packed weight rows per tile
+    static constexpr int BN = TF * MP;                   // MMA N = packed weight rows per tile
+    static_assert(FPT >= 1 && FPT * EWG == TF, "too many epilogue warpgroups for this bin count");
     static constexpr int YG = TF >= 4 ? 1 : 4 / TF;      // column tiles per fp32 output store (rows of >= 16 bytes)
     static constexpr int YROW = YG * TF;                 // floats per staged row: 8 or 4
     static constexpr int YG16 = 8 / TF;                  // column tiles per pair output store
     static constexpr int YROW16 = 8;                     // halfs per staged row (hi rows, then lo rows)
     static_assert(BN % 16 == 0 && BN <= STEP_BN_MAX && 2 * MP <= STEP_BN_MAX, "unsupported bin count for the coupling-step kernel");
     static_assert(BM * YROW * 4 <= STEP_Y_BUF_BYTES && 2 * BM * YROW16 * 2 <= STEP_Y_BUF_BYTES, "staging buffer");
+    static_assert(128 * EWG * FPT * 4 <= STEP_X_BYTES && (EWG - 1) * 128 * 4 <= STEP_X_BYTES, "x staging");
 };
 
 struct StepParams {
@@ -111,8 +116,8 @@ __device__ __forceinline__ void step_store_2d(const CUtensorMap* map, uint32_t s
                  : "memory");
 }
 
-template <int NB, bool TAILS, int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int NB, bool TAILS, int CL, int EWG>
+__global__ void __launch_bounds__(128 + 128 * EWG, 1)
 rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                         const __grid_constant__ CUtensorMap map_w0_hi, const __grid_constant__ CUtensorMap map_w0_lo,
                         const __grid_constant__ CUtensorMap map_wt_hi, const __grid_constant__ CUtensorMap map_wt_lo,
@@ -120,8 +125,10 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yh,
                         const __grid_constant__ CUtensorMap map_yl, const __grid_constant__ CUtensorMap map_h_hi,
                         const __grid_constant__ CUtensorMap map_h_lo, const StepParams p) {
-    using Cfg = StepCfg<NB, TAILS>;
+    using Cfg = StepCfg<NB, TAILS, EWG>;
     constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HC, BN = Cfg::BN, TF = Cfg::TF;
+    constexpr int NEPI = 4 * EWG;                  // epilogue warps
+    constexpr int CT = BN_MAX / EWG;               // trunk-layer columns per epilogue thread
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -134,8 +141,8 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const uint32_t bar_outready = bars + 120;     // trunk_only: ... the trunk's output, ready for the TMA stores
     const uint32_t bar_bfull = bars + 128, bar_bempty = bars + 144;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STEP_BAR_OFF + 160);
-    float* s_lad = reinterpret_cast<float*>(smem_gen + STEP_LAD_OFF);
-    float* s_bias = reinterpret_cast<float*>(smem_gen + STEP_BIAS_OFF);        // [2][256]
+    float* s_bias = reinterpret_cast<float*>(smem_gen + STEP_BIAS_OFF);        // [2][STEP_BN_MAX]
+    float* s_lad = reinterpret_cast<float*>(smem_gen + STEP_X_OFF);            // [EWG-1][128], aliases the (then idle) x staging
 
     uint32_t tid_x;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_x));
@@ -150,9 +157,9 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 
     if (tid_x == 0) {
         for (int s = 0; s < STEP_NBAR; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
-        mbar_init(bar_aready, 8); mbar_init(bar_outready, 8);
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_bfull + 8 * b, 1); mbar_init(bar_bempty + 8 * b, 8); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI); }
+        mbar_init(bar_aready, NEPI); mbar_init(bar_outready, NEPI);
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_bfull + 8 * b, 1); mbar_init(bar_bempty + 8 * b, NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w0_hi); prefetch_tmap(&map_w0_lo);
         prefetch_tmap(&map_wt_hi); prefetch_tmap(&map_wt_lo); prefetch_tmap(&map_wf_hi); prefetch_tmap(&map_wf_lo);
@@ -261,7 +268,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                                 const int cols = min(BN, p.d_t * MP - n * BN);
                                 mbar_wait(bar_bempty + 8 * bslot, bphase ^ 1);
                                 mbar_expect_tx(bar_bfull + 8 * bslot, (uint32_t)cols * 4u);
-                                bulk_load_1d(smem_u32(s_bias + bslot * 256), p.bias + (int64_t)n * BN, (uint32_t)cols * 4u,
+                                bulk_load_1d(smem_u32(s_bias + bslot * STEP_BN_MAX), p.bias + (int64_t)n * BN, (uint32_t)cols * 4u,
                                              bar_bfull + 8 * bslot);
                                 if (++bslot == 2) { bslot = 0; bphase ^= 1; }
                             }
@@ -425,35 +432,52 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-        // ================================================= accumulate + epilogues: 8 warps.  Thread = one row of the tile
-        // (TMEM lane) x one half of the columns.
+        if (EWG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");   // 640 x 96 at launch; the control warpgroup frees 56 x 128
+        // ================================================= accumulate + epilogues: 4 * EWG warps.  Thread = one row of the tile
+        // (TMEM lane) x one 1/EWG share of the columns.
         const int q = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int wg = (warp - 4) >> 2;
         const int r_tile = q * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         int flag = 0;
         int bslot = 0; uint32_t bphase = 0;
         int ybuf = 0;
         float4* skip = p.skip_buf + (size_t)blockIdx.x * (size_t)(p.H / 4) * 128 + r_tile;       // [c4 * 128]: coalesced across lanes
+        float* s_x = reinterpret_cast<float*>(smem_gen + STEP_X_OFF) + (tid_x - 128) * FPT;     // this thread's staged inputs
         for (int u = first; u < units; u += step) {
             const int m = u * CL + cta_rank;
             const int64_t row = (int64_t)m * BM + r_tile;
             const bool row_ok = row < p.n_rows;
+            // Inputs of the FPT features this thread owns in column tile n -> its shared-memory slot, asynchronously (LDGSTS): a
+            // register prefetch was spilled by the compiler and the store waited for the load (ncu, r2: 22 % of the epilogue
+            // warps' samples).  Issued one tile ahead (tile 0: before the trunk); read back by the same thread.
+            auto prefetch_x = [&](int n) {
+                const int jn = (n * EWG + wg) * FPT;
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) {
+                    if (row_ok && jn + f < p.d_t) {
+                        const int cf = p.t_cols ? __ldg(p.t_cols + jn + f) : p.t_col0 + jn + f;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_x + f)), "l"(p.x + row * p.ldx + cf) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            if (!p.trunk_only) prefetch_x(0);
             // ------------------------------------------------ conditioner trunk: layer l's epilogue writes layer l+1's operand into R
             for (int l = 0; l < p.num_layers; ++l) {
                 const int lf = p.layer_flags[l];
                 const bool last = l == p.num_layers - 1;
-                const int n0 = half * HALF;
-                float sum[HALF];
+                const int n0 = wg * CT;
+                float sum[CT];
 #pragma unroll
-                for (int c = 0; c < HALF; c += 4) {
+                for (int c = 0; c < CT; c += 4) {
                     float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if ((lf & SL_ADD_SKIP) && n0 + c < p.H) r4 = skip[(size_t)((n0 + c) >> 2) * 128];
                     sum[c] = r4.x; sum[c + 1] = r4.y; sum[c + 2] = r4.z; sum[c + 3] = r4.w;
                 }
 #pragma unroll
-                for (int c = 0; c < HALF; c += 4) {
+                for (int c = 0; c < CT; c += 4) {
                     if (n0 + c < p.H) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias_trunk + l * p.H + n0 + c));
                         sum[c] += b4.x; sum[c + 1] += b4.y; sum[c + 2] += b4.z; sum[c + 3] += b4.w;
@@ -461,20 +485,21 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 }
                 const float as = p.acc_scale[l], ias = p.inv_acc_scale[l];
 #pragma unroll
-                for (int c = 0; c < HALF; ++c) sum[c] *= as;
+                for (int c = 0; c < CT; ++c) sum[c] *= as;
                 const int groups = l == 0 ? groups0 : groupsh;
                 for (int g = 0; g < groups; ++g) {
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HALF;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + wg * CT;
+                    constexpr int LD = EWG == 2 ? 2 : 1;               // 32-column TMEM loads in flight per wait (register budget)
 #pragma unroll
-                    for (int c = 0; c < HALF; c += 64) {
-                        uint32_t raw[2][32];
-                        tmem_ld32(taddr + c, raw[0]);
-                        tmem_ld32(taddr + c + 32, raw[1]);
+                    for (int c = 0; c < CT; c += 32 * LD) {
+                        uint32_t raw[LD][32];
+#pragma unroll
+                        for (int v = 0; v < LD; ++v) tmem_ld32(taddr + c + 32 * v, raw[v]);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int v = 0; v < 2; ++v) {
+                        for (int v = 0; v < LD; ++v) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 2) {
                                 const float2 r2 = __fadd2_rn(make_float2(sum[c + 32 * v + j], sum[c + 32 * v + j + 1]),
@@ -492,20 +517,20 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 // ---- layer epilogue.  Every MMA of this layer has retired (its last partial sum was drained), so R may be
                 // overwritten with the next layer's operand.
 #pragma unroll
-                for (int c = 0; c < HALF; ++c) {
+                for (int c = 0; c < CT; ++c) {
                     float x = sum[c] * ias;
                     if (lf & SL_RELU_OUT) x = fmaxf(x, 0.0f);
                     sum[c] = x;
                 }
                 if (lf & SL_SAVE_SKIP) {
 #pragma unroll
-                    for (int c = 0; c < HALF; c += 4)
+                    for (int c = 0; c < CT; c += 4)
                         if (n0 + c < p.H) skip[(size_t)((n0 + c) >> 2) * 128] = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
                 }
                 float amax = 0.0f;
 #pragma unroll
-                for (int s = 0; s < HALF / BK; ++s) {                 // 4 K-slabs of 32 columns per thread
-                    const int slab = half * (HALF / BK) + s;
+                for (int s = 0; s < CT / BK; ++s) {                   // CT / 32 K-slabs of 32 columns per thread
+                    const int slab = wg * (CT / BK) + s;
                     if (slab < num_kh) {
                         uint8_t* base = smem_gen + slab * STEP_SLAB_BYTES + r_tile * ROW_BYTES;
 #pragma unroll
@@ -535,27 +560,15 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
             if (p.trunk_only) continue;
             // ------------------------------------------------ final layer + spline: the column tiles of this row block
             float lad_row = 0.0f;
-            float xin[FPT], xin_next[FPT];
-            int col[FPT], col_next[FPT];
-            auto load_x = [&](int n, float (&xv)[FPT], int (&cv)[FPT]) {
-                const int jn = (n * 2 + half) * FPT;
-#pragma unroll
-                for (int f = 0; f < FPT; ++f) {
-                    const bool ok = row_ok && (jn + f < p.d_t);
-                    cv[f] = !ok ? 0 : (p.t_cols ? __ldg(p.t_cols + jn + f) : p.t_col0 + jn + f);
-                    xv[f] = ok ? p.x[row * p.ldx + cv[f]] : 0.0f;
-                }
-            };
-            load_x(0, xin, col);
             for (int n = 0; n < p.num_n_tiles; ++n) {
-                const int j0 = (n * 2 + half) * FPT;                       // first feature this thread owns in this tile
+                const int j0 = (n * EWG + wg) * FPT;                       // first feature this thread owns in this tile
                 float sum[HC];
 #pragma unroll
                 for (int c = 0; c < HC; ++c) sum[c] = 0.0f;
                 for (int g = 0; g < groupsf; ++g) {
                     mbar_wait(bar_tfull + 8 * acc, acc_phase);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HC;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + wg * HC;
                     constexpr int LDB = HC <= 48 ? 3 : 4;           // TMEM loads in flight per wait
 #pragma unroll
                     for (int c = 0; c < HC; c += 8 * LDB) {
@@ -581,11 +594,16 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                if (n + 1 < p.num_n_tiles) load_x(n + 1, xin_next, col_next);
+                // ---- this tile's inputs out of the staging slot, the next tile's on their way into it
+                float xin[FPT];
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                for (int f = 0; f < FPT; ++f) xin[f] = (row_ok && j0 + f < p.d_t) ? s_x[f] : 0.0f;
+                if (n + 1 < p.num_n_tiles) prefetch_x(n + 1);
                 // ---- back from the accumulators' power-of-two scaled domain, plus the packed bias staged in shared memory
                 {
                     mbar_wait(bar_bfull + 8 * bslot, bphase);
-                    const float4* bias4 = reinterpret_cast<const float4*>(s_bias + bslot * 256 + half * HC);
+                    const float4* bias4 = reinterpret_cast<const float4*>(s_bias + bslot * STEP_BN_MAX + wg * HC);
 #pragma unroll
                     for (int c = 0; c < HC; c += 4) {
                         const float4 b4 = (j0 + c / MP < p.d_t) ? bias4[c >> 2] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -611,7 +629,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     if (p.pair_only) {
                         __half* sh = reinterpret_cast<__half*>(buf);
                         __half* sl = sh + BM * YROW16;
-                        const int off = r_tile * YROW16 + (n % YG16) * TF + half * FPT;
+                        const int off = r_tile * YROW16 + (n % YG16) * TF + wg * FPT;
 #pragma unroll
                         for (int f = 0; f < FPT; ++f) {
                             __half hi, lo;
@@ -622,7 +640,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                             if (row_ok && j0 + f < p.d_t) { lad_row += ll[f]; flag |= f2; }
                         }
                     } else {
-                        float* dst = reinterpret_cast<float*>(buf) + r_tile * YROW + (n % YG) * TF + half * FPT;
+                        float* dst = reinterpret_cast<float*>(buf) + r_tile * YROW + (n % YG) * TF + wg * FPT;
 #pragma unroll
                         for (int f = 0; f < FPT; ++f) {
                             dst[f] = yy[f];
@@ -631,7 +649,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     }
                     if (n % grp == grp - 1 || n == p.num_n_tiles - 1) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("bar.sync 2, 256;" ::: "memory");
+                        asm volatile("bar.sync 2, %0;" ::"n"(128 * EWG) : "memory");
                         if (issuer) {
                             const uint32_t src = smem_base + STEP_Y_OFF + ybuf * STEP_Y_BUF_BYTES;
                             if (p.pair_only) {
@@ -650,21 +668,25 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
 #pragma unroll
                     for (int f = 0; f < FPT; ++f) {
                         if (row_ok && j0 + f < p.d_t) {
-                            p.y[row * p.ldy + col[f]] = yy[f];
+                            const int cf = p.t_cols ? __ldg(p.t_cols + j0 + f) : p.t_col0 + j0 + f;
+                            p.y[row * p.ldy + cf] = yy[f];
                             lad_row += ll[f];
                         }
                     }
                 }
-#pragma unroll
-                for (int f = 0; f < FPT; ++f) { xin[f] = xin_next[f]; col[f] = col_next[f]; }
                 __syncwarp();
             }
-            // ---- finish the row block: lad_accum[row] += the two warpgroups' partial sums, fixed order
+            // ---- finish the row block: lad_accum[row] += the warpgroups' partial sums, fixed order (the x staging is idle here)
             if (p.lad_accum) {
-                if (half == 1) s_lad[r_tile] = lad_row;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0 && row_ok) p.lad_accum[row] += lad_row + s_lad[r_tile];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (wg > 0) s_lad[(wg - 1) * 128 + r_tile] = lad_row;
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * EWG) : "memory");
+                if (wg == 0 && row_ok) {
+                    float t = lad_row;
+#pragma unroll
+                    for (int h = 1; h < EWG; ++h) t += s_lad[(h - 1) * 128 + r_tile];
+                    p.lad_accum[row] += t;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * EWG) : "memory");
             }
         }
         if (warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging outlives its stores
@@ -676,9 +698,9 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-template <int NB, bool TAILS>
+template <int NB, bool TAILS, int EWG>
 static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st) {
-    using Cfg = StepCfg<NB, TAILS>;
+    using Cfg = StepCfg<NB, TAILS, EWG>;
     static int cluster_pref = 0;
     if (!cluster_pref) {
         const char* e = getenv("NFK_CLUSTER");
@@ -686,7 +708,9 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
     }
     const int H = p.H;
     const int nch = H > 128 ? 2 : 1, ch = H / nch;
-    const int CL = (cluster_pref == 2 && p.num_m_tiles >= 2 && ch % 16 == 0 && (ch / 2) % 8 == 0) ? 2 : 1;
+    // trunk-only launches run single CTAs: their TMA stores read R while a cluster peer could already multicast the next
+    // tile's weights over it
+    const int CL = (cluster_pref == 2 && !p.trunk_only && p.num_m_tiles >= 2 && ch % 16 == 0 && (ch / 2) % 8 == 0) ? 2 : 1;
     const int L = p.num_layers - 1;
     CUtensorMap ma_hi, ma_lo, mw0_hi, mw0_lo, mwt_hi, mwt_lo, mwf_hi, mwf_lo;
     int rc;
@@ -723,14 +747,20 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
     const int grid = CL * (units < max_clusters ? units : max_clusters);
     NFK_REQUIRE(d->workspace_bytes >= (size_t)grid * (size_t)H * 128 * 4, "workspace too small: %zu bytes given, %zu needed",
                 d->workspace_bytes, (size_t)grid * (size_t)H * 128 * 4);
-    auto kern1 = rq_coupling_step_kernel<NB, TAILS, 1>;
-    auto kern2 = rq_coupling_step_kernel<NB, TAILS, 2>;
-    cudaError_t e = cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES);
-    if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", STEP_SMEM_BYTES, cudaGetErrorString(e));
+    auto kern1 = rq_coupling_step_kernel<NB, TAILS, 1, EWG>;
+    auto kern2 = rq_coupling_step_kernel<NB, TAILS, 2, EWG>;
+    cudaError_t e = cudaSuccess;
+    static DeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
+        e = cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", STEP_SMEM_BYTES, cudaGetErrorString(e));
+        attr_once.mark(attr_dev);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(128 + 128 * EWG);
     cfg.dynamicSmemBytes = STEP_SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -742,6 +772,16 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
                   : cudaLaunchKernelEx(&cfg, kern1, ma_hi, ma_lo, mw0_hi, mw0_lo, mwt_hi, mwt_lo, mwf_hi, mwf_lo, my, myh, myl, mh_hi, mh_lo, p);
     if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(rq_coupling_step_kernel, cluster %d): %s", CL, cudaGetErrorString(e));
     return check_launch("rq_coupling_step_kernel");
+}
+
+// epilogue warpgroups: NFK_STEP_EWG=2 selects the two-warpgroup variant (A/B measurements), default four
+static int step_ewg() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("NFK_STEP_EWG");
+        v = (e && e[0] == '2') ? 2 : 4;
+    }
+    return v;
 }
 
 }  // namespace tc
@@ -796,7 +836,7 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
     cudaStream_t st = (cudaStream_t)stream;
     if (trunk_only) {
         NFK_REQUIRE(d->h_lo && d->ldh % 8 == 0 && aligned16(d->h_hi) && aligned16(d->h_lo), "bad trunk output pair");
-        return tc::launch_step<8, true>(d, p, st);
+        return tc::step_ewg() == 4 ? tc::launch_step<8, true, 4>(d, p, st) : tc::launch_step<8, true, 2>(d, p, st);
     }
     int rc = make_spline_params(d->spline, &p.sp);
     if (rc) return rc;
@@ -811,7 +851,11 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
     p.inv_acc_scale_f = ldexpf(1.0f, -(d->act_exp + d->wp_exp));
     p.pair_only = d->y_hi ? 1 : 0; p.out_scale = ldexpf(1.0f, d->y_exp);
     const bool tails = d->spline->linear_tails != 0;
-#define NFK_STEP(NB) return tails ? tc::launch_step<NB, true>(d, p, st) : tc::launch_step<NB, false>(d, p, st)
+    // four epilogue warpgroups where a column tile has at least four features, else two
+#define NFK_STEP(NB)                                                                                                       \
+    if (tc::step_ewg() == 4 && tc::StepCfg<NB, true, 2>::TF >= 4 && tails) return tc::launch_step<NB, true, tc::StepCfg<NB, true, 2>::TF >= 4 ? 4 : 2>(d, p, st);     \
+    if (tc::step_ewg() == 4 && tc::StepCfg<NB, false, 2>::TF >= 4 && !tails) return tc::launch_step<NB, false, tc::StepCfg<NB, false, 2>::TF >= 4 ? 4 : 2>(d, p, st);  \
+    return tails ? tc::launch_step<NB, true, 2>(d, p, st) : tc::launch_step<NB, false, 2>(d, p, st)
     switch (d->spline->num_bins) {
         case 4: NFK_STEP(4);
         case 8: NFK_STEP(8);

@@ -617,12 +617,14 @@ int make_map(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t 
 }
 
 int sm_count() {
-    static int n = 0;
+    static std::atomic<int> counts[64];                      // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = counts[dev & 63].load(std::memory_order_relaxed);
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        counts[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
 }
@@ -712,13 +714,14 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
         if (y_hi && w1 % 64 && (rc = tc::make_store_map(&mylt, y_lo, true, n_rows, pn, lds, w1 % 64))) return rc;
     }
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::LIN_SMEM_BYTES, cudaGetErrorString(e));
-        attr_set = true;
+        attr_once.mark(attr_dev);
     }
     const int units = (p.num_m_tiles + CL - 1) / CL;
     p.n_inner = 0;   // measured r1: walking the column tiles of a row block back to back did not help

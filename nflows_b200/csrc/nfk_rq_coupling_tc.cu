@@ -475,11 +475,12 @@ static int launch_fused_cl(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, c
         if ((rc = make_out_map16(&myh, pair_hi, p.n_rows, p.t_col0 + p.d_t, pair_lds, Cfg::YROW16, BM))) return rc;
         if ((rc = make_out_map16(&myl, pair_lo, p.n_rows, p.t_col0 + p.d_t, pair_lds, Cfg::YROW16, BM))) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(rq_coupling_final_kernel<NB, TAILS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", smem, cudaGetErrorString(e));
-        attr_set = true;
+        attr_once.mark(attr_dev);
     }
     const int blocks = (p.num_m_tiles + CL - 1) / CL;
     const int max_clusters = sm_count() / CL;

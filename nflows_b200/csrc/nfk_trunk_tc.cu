@@ -375,13 +375,14 @@ extern "C" int nfk_residual_trunk_f16x3(const void* a_hi_, const void* a_lo_, in
     if ((rc = tc::make_map(&my_hi, y_hi, n_rows, hidden_features, lds, tc::BM))) return rc;
     if ((rc = tc::make_map(&my_lo, y_lo, n_rows, hidden_features, lds, tc::BM))) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    int attr_dev = 0;
+    if (attr_once.pending(&attr_dev)) {
         cudaError_t e = cudaFuncSetAttribute(tc::residual_trunk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TRUNK_SMEM_BYTES);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(tc::residual_trunk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TRUNK_SMEM_BYTES);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::TRUNK_SMEM_BYTES, cudaGetErrorString(e));
-        attr_set = true;
+        attr_once.mark(attr_dev);
     }
     const int units = (p.num_m_tiles + CL - 1) / CL;
     const int max_clusters = tc::sm_count() / CL;

@@ -19,6 +19,11 @@ def backend():
     return os.environ.get("NFLOWS_B200_GEMM", "tc")
 
 
+def cache_epoch():
+    from . import config
+    return config.cache_epoch
+
+
 def act_exp():
     from . import config
     return int(config.activation_exp)
@@ -28,7 +33,7 @@ def split_weight(weight):
     """Pair16 of a weight matrix (scaled so that max |w| sits at 2^14), cached until the parameter is modified."""
     w = weight.detach()
     key = id(weight)
-    sig = (w.data_ptr(), w._version, str(w.device), tuple(w.shape))
+    sig = (w.data_ptr(), w._version, str(w.device), tuple(w.shape), cache_epoch())
     hit = _SPLIT_CACHE.get(key)
     if hit is None or hit[0] != sig:
         if not w.is_contiguous():
@@ -97,7 +102,7 @@ def pack_trunk(body_tail):
     """Stacked fp16 pairs, per-layer exponents and stacked biases of the layers the trunk kernel runs; cached per version."""
     key = tuple(id(layer[0]) for layer in body_tail)
     sig = tuple((layer[0].data_ptr(), layer[0]._version, layer[1].data_ptr(), layer[1]._version, str(layer[0].device))
-                for layer in body_tail)
+                for layer in body_tail) + (cache_epoch(),)
     hit = _TRUNK_CACHE.get(key)
     if hit is None or hit[0] != sig:
         h = body_tail[0][0].shape[0]
@@ -190,7 +195,7 @@ def step_plan(chain):
     body = chain[:-1]
     key = tuple(id(layer[0]) for layer in body)
     sig = tuple((layer[0].data_ptr(), layer[0]._version, layer[1].data_ptr(), layer[1]._version, str(layer[0].device))
-                for layer in body) + (act_exp(),)
+                for layer in body) + (act_exp(), cache_epoch())
     hit = _STEP_CACHE.get(key)
     if hit is None or hit[0] != sig:
         flags = plan_step_kernel(chain)
@@ -315,7 +320,7 @@ def pack_final_spline(weight, bias, d_t, m, mp):
     into a Pair16; bias packed the same way (fp32).  Cached until weight or bias is modified."""
     w, b = weight.detach(), bias.detach()
     key = id(weight)
-    sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, str(w.device), d_t, m, mp)
+    sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, str(w.device), d_t, m, mp, cache_epoch())
     hit = _PACK_CACHE.get(key)
     if hit is None or hit[0] != sig:
         k = w.shape[1]

@@ -32,7 +32,8 @@ class StandardNormal(Distribution):
             flat = inputs.reshape(inputs.shape[0], int(np.prod(self._shape)))
             if flat.stride(-1) != 1:
                 flat = flat.contiguous()
-            return K.std_normal_log_prob(flat, self._log_z_host, logabsdet)
+            with K.on_device_of(flat):
+                return K.std_normal_log_prob(flat, self._log_z_host, logabsdet)
         neg_energy = -0.5 * torchutils.sum_except_batch(inputs ** 2, num_batch_dims=1)
         log_prob = neg_energy - self._log_z
         return log_prob if logabsdet is None else log_prob + logabsdet

@@ -35,9 +35,34 @@ def _rows2d(t, name):
     return t
 
 
-def native_ok(t):
-    """True when `t` is something the native path takes: CUDA, fp32, no autograd graph to build."""
-    return t.is_cuda and t.dtype == torch.float32 and not (torch.is_grad_enabled() and t.requires_grad)
+def native_ok(t, context=None):
+    """True when `t` is something the native path takes: CUDA, fp32, no autograd graph to build -- neither through `t` nor
+    through a context tensor (the kernels take raw pointers: a graph to the context / embedding net would be dropped)."""
+    if not (t.is_cuda and t.dtype == torch.float32):
+        return False
+    if torch.is_grad_enabled() and (t.requires_grad or (torch.is_tensor(context) and context.requires_grad)):
+        return False
+    return True
+
+
+def on_device_of(t):
+    """Context manager: make t's device current, so the launches below go to its current stream and every per-device
+    resource (function attributes, SM count, workspaces) is the right one.  Every native entry point runs under it."""
+    return torch.cuda.device(t.device)
+
+
+_warned_eager = [False]
+
+
+def warn_eager_cuda(t, module=None):
+    """One warning when a CUDA fp32 call takes the differentiable PyTorch path only because autograd is on."""
+    if _warned_eager[0] or not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and torch.is_grad_enabled()):
+        return
+    _warned_eager[0] = True
+    import warnings
+    warnings.warn("nflows_b200: this CUDA call runs the differentiable PyTorch formulation, not the native kernels, because "
+                  "autograd is enabled and the inputs or parameters require grad; wrap inference in torch.no_grad() (or freeze "
+                  "the parameters) to run the sm_100a kernels.", RuntimeWarning, stacklevel=3)
 
 
 def new_flags(device):

@@ -133,7 +133,7 @@ class MaskedPiecewiseRationalQuadraticAutoregressiveTransform(AutoregressiveTran
 
     # ---- native ----------------------------------------------------------------------------------------------------
     def _native_ready(self, inputs, context):
-        return (K.native_ok(inputs) and inputs.dim() == 2 and context is None and params_frozen(self)
+        return (K.native_ok(inputs, context) and inputs.dim() == 2 and context is None and params_frozen(self)
                 and self.num_bins <= 64 and self.autoregressive_net.dense_chain(None) is not None)
 
     def _spline_desc(self):

@@ -40,6 +40,12 @@ class Transform(nn.Module):
     def inverse(self, inputs, context=None):
         return self._run(inputs, context, inverse=True)
 
+    def train(self, mode=True):
+        # derived-weight caches are keyed on tensor versions, which writes through `.data` do not bump: a mode switch (what
+        # follows an EMA weight swap) invalidates them (see nflows_b200.invalidate_native_caches)
+        config.cache_epoch += 1
+        return super().train(mode)
+
     # -- subclass hooks ---------------------------------------------------------------------------------
     def _eager(self, inputs, context, inverse):
         if inverse:
@@ -55,13 +61,15 @@ class Transform(nn.Module):
     # -- dispatch ---------------------------------------------------------------------------------------
     def _run(self, inputs, context, inverse):
         if torch.is_tensor(inputs) and self._native_ready(inputs, context):
-            x = inputs if inputs.stride(-1) == 1 else inputs.contiguous()
-            lad = K.zeros_lad(x)
-            flags = K.new_flags(x.device)
-            out = self._native_apply(x, lad, flags, inverse, context)
-            if config.check_domain:
-                K.raise_for_flags(flags)
+            with K.on_device_of(inputs):
+                x = inputs if inputs.stride(-1) == 1 else inputs.contiguous()
+                lad = K.zeros_lad(x)
+                flags = K.new_flags(x.device)
+                out = self._native_apply(x, lad, flags, inverse, context)
+                if config.check_domain:
+                    K.raise_for_flags(flags)
             return out, lad
+        K.warn_eager_cuda(inputs)
         return self._eager(inputs, context, inverse)
 
 
@@ -96,7 +104,7 @@ class CompositeTransform(Transform):
         return outputs, total
 
     def _native_ready(self, inputs, context):
-        return K.native_ok(inputs) and inputs.dim() == 2 and params_frozen(self)
+        return K.native_ok(inputs, context) and inputs.dim() == 2 and params_frozen(self)
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
         """Walks the flattened leaves.  Between leaves the tensor may live in a permuted COLUMN LAYOUT (fused_affine.Layout):

@@ -89,7 +89,7 @@ class CouplingTransform(Transform):
 
     # ---- native path --------------------------------------------------------------------------------------
     def _native_ready(self, inputs, context):
-        return K.native_ok(inputs) and inputs.dim() == 2 and params_frozen(self) and self._native_epilogue_supported()
+        return K.native_ok(inputs, context) and inputs.dim() == 2 and params_frozen(self) and self._native_epilogue_supported()
 
     def _native_epilogue_supported(self):
         return False

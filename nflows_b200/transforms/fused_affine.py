@@ -34,13 +34,16 @@ class Layout:
 def is_affine_leaf(leaf, x):
     from .lu import LULinear
     from .normalization import ActNorm
-    from .permutations import Permutation
+    from .permutations import Permutation, RandomPermutation, ReversePermutation
 
-    if isinstance(leaf, ActNorm):
+    # exact types (and RandomPermutation / ReversePermutation, which only choose the index vector): a subclass that overrides
+    # forward / inverse -- OneByOneConvolution(LULinear) with its own permutation and 4-D check, user subclasses -- is not
+    # the plain affine map that gets folded
+    if type(leaf) is ActNorm:
         return x.dim() == 2 and not (leaf.training and not bool(leaf.initialized))
-    if isinstance(leaf, Permutation):
+    if type(leaf) in (Permutation, RandomPermutation, ReversePermutation):
         return leaf._dim == 1
-    return isinstance(leaf, LULinear)
+    return type(leaf) is LULinear
 
 
 def _signature(leaves):
@@ -122,7 +125,7 @@ class AffineRun:
 
     @classmethod
     def cached(cls, cache, leaves, device):
-        sig = (_signature(leaves), str(device))
+        sig = (_signature(leaves), str(device), D.cache_epoch())
         key = tuple((id(leaf), inv) for leaf, inv in leaves)
         hit = cache.get(key)
         if hit is None or hit[0] != sig:

@@ -65,7 +65,7 @@ class LULinear(Linear):
 
     # ---- native: one dense layer with the folded weight (see fused_affine.py) -----------------------------
     def _native_ready(self, inputs, context):
-        return K.native_ok(inputs) and inputs.dim() == 2 and params_frozen(self)
+        return K.native_ok(inputs, context) and inputs.dim() == 2 and params_frozen(self)
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
         from .fused_affine import AffineRun

@@ -50,7 +50,8 @@ class MaskedLinear(nn.Linear):
 
     def masked_weight(self):
         """weight * mask as a tensor object that stays the same until the weight changes (so split-operand caches hit)."""
-        sig = (self.weight.data_ptr(), self.weight._version, str(self.weight.device))
+        from .. import config
+        sig = (self.weight.data_ptr(), self.weight._version, str(self.weight.device), config.cache_epoch)
         if self._masked_cache is None or self._masked_cache[0] != sig:
             self._masked_cache = (sig, (self.weight.detach() * self.mask).contiguous())
         return self._masked_cache[1]

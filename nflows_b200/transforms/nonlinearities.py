@@ -39,7 +39,7 @@ class PiecewiseRationalQuadraticCDF(Transform):
             self.unnormalized_derivatives = nn.Parameter(torch.rand(*shape, num_derivatives))
 
     def _native_ready(self, inputs, context):
-        return (K.native_ok(inputs) and params_frozen(self) and self.tails in (None, "linear")
+        return (K.native_ok(inputs, context) and params_frozen(self) and self.tails in (None, "linear")
                 and inputs.shape[1:] == self.unnormalized_widths.shape[:-1] and self.unnormalized_widths.shape[-1] <= 64)
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
@@ -60,12 +60,13 @@ class PiecewiseRationalQuadraticCDF(Transform):
     def _run(self, inputs, context, inverse):
         # same dispatch as Transform._run, but inputs may have any number of event dimensions
         if torch.is_tensor(inputs) and self._native_ready(inputs, context):
-            x = inputs.contiguous()
-            lad = K.zeros_lad(x)
-            flags = K.new_flags(x.device)
-            out = self._native_apply(x, lad, flags, inverse, context)
-            if config.check_domain:
-                K.raise_for_flags(flags)
+            with K.on_device_of(inputs):
+                x = inputs.contiguous()
+                lad = K.zeros_lad(x)
+                flags = K.new_flags(x.device)
+                out = self._native_apply(x, lad, flags, inverse, context)
+                if config.check_domain:
+                    K.raise_for_flags(flags)
             return out, lad
         return self._eager(inputs, context, inverse)
 

@@ -29,7 +29,7 @@ class ActNorm(Transform):
         return self.training and not bool(self.initialized)
 
     def _native_ready(self, inputs, context):
-        return K.native_ok(inputs) and inputs.dim() == 2 and params_frozen(self) and not self._needs_init()
+        return K.native_ok(inputs, context) and inputs.dim() == 2 and params_frozen(self) and not self._needs_init()
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
         total = float(torch.sum(self.log_scale.detach()))

@@ -39,7 +39,7 @@ class Permutation(Transform):
             raise ValueError("Dimension {} in inputs must be of size {}.".format(self._dim, len(self._permutation)))
 
     def _native_ready(self, inputs, context):
-        return K.native_ok(inputs) and inputs.dim() == 2 and self._dim == 1
+        return K.native_ok(inputs, context) and inputs.dim() == 2 and self._dim == 1
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
         self._check(inputs)

@@ -31,12 +31,13 @@ def _use_native(inputs, *params):
 
 def _native_call(desc, inverse, inputs, uw, uh, ud):
     lead = inputs.shape
-    flags = K.new_flags(inputs.device)
-    k = uw.shape[-1]
-    y, lad = K.rqs_elementwise(desc, inverse, inputs, uw.expand(*lead, k), uh.expand(*lead, k),
-                               ud.expand(*lead, ud.shape[-1]), flags=flags)
-    if config.check_domain:
-        K.raise_for_flags(flags)
+    with K.on_device_of(inputs):
+        flags = K.new_flags(inputs.device)
+        k = uw.shape[-1]
+        y, lad = K.rqs_elementwise(desc, inverse, inputs, uw.expand(*lead, k), uh.expand(*lead, k),
+                                   ud.expand(*lead, ud.shape[-1]), flags=flags)
+        if config.check_domain:
+            K.raise_for_flags(flags)
     return y, lad
 
 
