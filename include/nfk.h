@@ -94,14 +94,16 @@ int nfk_linear(const float* X, int64_t ldx, const float* W, int64_t ldw, const f
  * fp32; the epilogue multiplies by 2^-(a_exp + w_exp).  Pick exp so that max |v| * 2^exp stays below 65000 and typical
  * values sit well above 2^-3 (weights: max |w| -> 2^14; activations: a fixed exponent such as 6).
  * The epilogue can emit the fp32 result Y and/or, for the first split_cols columns (0 = all), the split pair of Y (of
- * relu(Y) when split_relu) with exponent y_exp that the next layer consumes.  A pair element that leaves the fp16 range
+ * relu(Y) when split_relu) with exponent y_exp that the next layer consumes.  y_first_col > 0 says the fp32 result is only needed
+ * for columns >= y_first_col (the rest of Y may be left unwritten: a consumer that multiplies the pair never reads it).
+ * A pair element that leaves the fp16 range
  * raises NFK_FLAG_F16_RANGE in `flags`.  hi/lo pointers are fp16 device arrays, ld* in ELEMENTS; TMA needs in_features, lda,
  * ldw multiples of 8 and 16-byte aligned bases (nfk_linear_f16x3_supported). */
 int nfk_linear_f16x3_supported(int64_t lda, int64_t ldw, int32_t in_features);
 int nfk_linear_f16x3(const void* a_hi, const void* a_lo, int64_t lda, int32_t a_exp, const void* w_hi, const void* w_lo,
                      int64_t ldw, int32_t w_exp, const float* bias, const float* R, int64_t ldr, float* Y, int64_t ldy,
-                     void* y_hi, void* y_lo, int64_t lds, int32_t y_exp, int32_t split_cols, int relu_out, int split_relu,
-                     int64_t n_rows, int32_t in_features, int32_t out_features, int32_t* flags, void* stream);
+                     void* y_hi, void* y_lo, int64_t lds, int32_t y_exp, int32_t split_cols, int32_t y_first_col, int relu_out,
+                     int split_relu, int64_t n_rows, int32_t in_features, int32_t out_features, int32_t* flags, void* stream);
 /* hi[n, j], lo[n, j] = fp16 split pair of pre(x[n*ldx + j]) * 2^scale_exp, pre = relu if `relu`: weights (once per parameter
  * update), tensors entering a tensor-core chain from outside, the transformed half of a coupling output. */
 /* *out = max(*out, max |x[n, j]|) over an n_rows x n_cols matrix (NaNs skipped); *out must be >= 0 on entry.  Used to pick the

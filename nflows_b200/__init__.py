@@ -27,6 +27,9 @@ class _Config:
     #: dense layers: |a| * 2^exp must stay below 65000 (an overflow raises kernels.Float16RangeError) and |a| >= 2^-(3+exp)
     #: keeps the full 22-bit precision; 6 covers 2e-3 .. 1000
     activation_exp = 6
+    #: when a call trips the fp16 range flag, run it again with a smaller activation exponent (steps of 5, down to -24:
+    #: |a| up to 1e12) instead of raising -- the reference accepts any finite fp32 input; needs check_domain (the flag read)
+    auto_activation_exp = True
     #: rows per sub-block of a dense-layer chain: intermediates of a sub-block (split pairs, hidden activations) stay
     #: resident in the 126 MB L2 between consecutive kernels instead of round-tripping through HBM
     #: (measured r1: sub-blocks of 8-16 K rows are SLOWER -- 1-wave launches pay prologue/launch overhead; 256 K / 512 K / 1 M

@@ -61,7 +61,7 @@ _SIGNATURES = {
                            _P]),
     "nfk_linear_f16x3_supported": (c_int, [c_int64, c_int64, c_int32]),
     "nfk_linear_f16x3": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P, _P, c_int64, _P, c_int64, _P, _P, c_int64,
-                                 c_int32, c_int32, c_int, c_int, c_int64, c_int32, c_int32, _P, _P]),
+                                 c_int32, c_int32, c_int32, c_int, c_int, c_int64, c_int32, c_int32, _P, _P]),
     "nfk_absmax": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P]),
     "nfk_split_f16": (c_int, [_P, c_int64, c_int32, c_int, c_int32, _P, _P, c_int64, c_int64, _P, _P]),
     "nfk_residual_trunk_f16x3_supported": (c_int, [c_int32, c_int32, c_int64, c_int64]),

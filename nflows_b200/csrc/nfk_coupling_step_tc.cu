@@ -616,7 +616,8 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 }
                 // ---- spline on the FPT features held in registers
                 float yy[FPT], ll[FPT];
-                rqs_eval_multi<NB, TAILS, FPT, MP>(p.sp, p.inverse != 0, xin, sum, yy, ll, flag);
+                if (p.inverse) rqs_eval_lean<NB, TAILS, true, FPT, MP>(p.sp, xin, sum, yy, ll, flag);
+                else rqs_eval_lean<NB, TAILS, false, FPT, MP>(p.sp, xin, sum, yy, ll, flag);
                 const bool issuer = warp == 4 && lane == 0;
                 if (p.pair_only || p.tma_y) {
                     // Outputs leave through one of three staging buffers, one TMA store (pair: two) per group of YG column tiles.

@@ -32,7 +32,11 @@
 //                                128-byte chunks (SWIZZLE_128B, conflict-free) and one lane issues a TMA store per chunk --
 //                                full-line writes instead of the 32-sector scatter of a row-per-thread st.global (ncu, r1:
 //                                the epilogue warps spent 43 % of their samples waiting for the LSU to drain those stores)
-//   smem: 3 stages x (A_hi, A_lo, W_hi, W_lo) of K = 32 = 3 x 48 KB, + 8 warps x 2 x 4 KB store staging;
+//   smem: TWO operand rings -- A (activations, streamed from HBM: latency of microseconds under load) LIN_A_STAGES x 16 KB,
+//         W (weights, L2-resident) LIN_W_STAGES x 32 KB, each with its own producer thread and barriers, so the A stream runs
+//         4 K-slabs ahead of the MMAs while W needs only 2 (round 1 had ONE ring of 3 x 48 KB released in pairs of slabs: one
+//         load in flight, the tensor pipe waited a full HBM round trip per pair -- ncu r2: 21 % tensor, 39 % DRAM, 31 % L2);
+//         + 8 warps x 2 x 4 KB store staging;
 //   TMEM: 2 partial accumulators x 256 columns.
 #include <stdlib.h>
 
@@ -62,10 +66,19 @@ struct Params {
     int num_m_tiles, num_n_tiles;
     int n_inner;             // tile schedule, see tile_of()
     int tma_store;           // outputs are TMA-addressable (16-byte aligned bases and row pitches): staged stores
+    int y_first_col;         // the fp32 result is only needed for columns >= y_first_col (32-column chunks below it are skipped)
+    int a_stages;            // A ring depth
+    int w_slot_bytes;        // bytes per W ring slot (hi part first, lo part at w_slot_bytes / 2)
 };
 
-constexpr int LIN_STAGES = 3;
-constexpr int LIN_STG_OFF = LIN_STAGES * STAGE_BYTES + 1024;            // after the ring and the barrier block, 1024-aligned
+// Operand rings share LIN_RING_BYTES: LIN_W_STAGES weight slots of [W hi | W lo] sized for the launch's column tile (BN rows of
+// 64 bytes each, twice), the rest A slots of 16 KB [A hi | A lo] (BN = 208: 3 x 26 KB + 5 x 16 KB; BN = 256: 3 x 32 KB + 4 x 16 KB)
+constexpr int LIN_RING_BYTES = 160 * 1024;
+constexpr int LIN_A_STAGES_MAX = 8;
+constexpr int LIN_W_STAGES = 3;
+constexpr int LIN_A_STAGE_BYTES = 2 * A_BYTES;
+constexpr int LIN_BAR_OFF = LIN_RING_BYTES;
+constexpr int LIN_STG_OFF = LIN_BAR_OFF + 1024;                         // after the rings and the barrier block, 1024-aligned
 constexpr int LIN_STG_BYTES = 4096;                                     // one 32-row x 128-byte chunk
 constexpr int LIN_SMEM_BYTES = LIN_STG_OFF + 8 * 2 * LIN_STG_BYTES + 1024 /*alignment slack*/;
 
@@ -106,20 +119,24 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                      const __grid_constant__ CUtensorMap map_yl, const __grid_constant__ CUtensorMap map_y_tail,
                      const __grid_constant__ CUtensorMap map_yh_tail, const __grid_constant__ CUtensorMap map_yl_tail,
                      const Params p) {
-    constexpr int STAGES = LIN_STAGES;                                     // (shadows the 4-stage ring of the fused kernel)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t bars = smem_base + STAGES * STAGE_BYTES;                // 8-byte mbarriers
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES;
-    const uint32_t bar_tfull = bars + 16 * STAGES, bar_tempty = bars + 16 * STAGES + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 16 * STAGES + 32);
+    const int LIN_A_STAGES = p.a_stages;
+    const uint32_t LIN_W_STAGE_BYTES = (uint32_t)p.w_slot_bytes, W_LO = LIN_W_STAGE_BYTES / 2;
+    const uint32_t ring_w = smem_base + LIN_A_STAGES * LIN_A_STAGE_BYTES;
+    const uint32_t bars = smem_base + LIN_BAR_OFF;                         // 8-byte mbarriers
+    const uint32_t bar_afull = bars, bar_aempty = bars + 8 * LIN_A_STAGES_MAX;
+    const uint32_t bar_wfull = bars + 16 * LIN_A_STAGES_MAX, bar_wempty = bar_wfull + 8 * LIN_W_STAGES;
+    const uint32_t bar_tfull = bar_wempty + 8 * LIN_W_STAGES, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + LIN_BAR_OFF + 16 * LIN_A_STAGES_MAX + 16 * LIN_W_STAGES + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (p.K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+        for (int s = 0; s < LIN_A_STAGES; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < LIN_W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
@@ -136,84 +153,93 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");     // hand registers to the epilogue warpgroups
     if (warp == 0) {
-        // ================================================= TMA producer
+        // ================================================= TMA producer of the A ring (this CTA's 128 rows of every K-slab)
         if (lane == 0) {
-            const uint32_t tx_bytes = 2u * A_BYTES + 2u * (uint32_t)p.BN * ROW_BYTES;
+            int stage = 0; uint32_t phase = 0;
+            int tm, tn;
+            for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
+                const int m0 = tm * BM;
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(bar_aempty + 8 * stage, phase ^ 1);
+                    const uint32_t full = bar_afull + 8 * stage;
+                    const uint32_t sa = smem_base + stage * LIN_A_STAGE_BYTES;
+                    mbar_expect_tx(full, 2u * A_BYTES);
+                    tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
+                    tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
+                    if (++stage == LIN_A_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================================================= TMA producer of the W ring (each CTA of a cluster fetches half of every
+        // weight slab and multicasts it to both)
+        if (lane == 0) {
+            const uint32_t tx_bytes = 2u * (uint32_t)p.BN * ROW_BYTES;
             int stage = 0; uint32_t phase = 0;
             int tm, tn;
             const int wrows = p.BN / CL;                                   // weight rows this CTA fetches per slab
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
-                const int m0 = tm * BM;
                 const int n0 = tn * p.BN;
                 for (int ks = 0; ks < num_k; ++ks) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);           // every CTA of the cluster has released the slot
-                    const uint32_t full = bar_full + 8 * stage;
-                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    mbar_wait(bar_wempty + 8 * stage, phase ^ 1);          // every CTA of the cluster has released the slot
+                    const uint32_t full = bar_wfull + 8 * stage;
+                    const uint32_t sw = ring_w + stage * LIN_W_STAGE_BYTES;
                     mbar_expect_tx(full, tx_bytes);
-                    tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
-                    tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
                     if (CL == 1) {
-                        tma_load_2d(sa + 2 * A_BYTES, &map_w_hi, full, ks * BK, n0);
-                        tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, full, ks * BK, n0);
+                        tma_load_2d(sw, &map_w_hi, full, ks * BK, n0);
+                        tma_load_2d(sw + W_LO, &map_w_lo, full, ks * BK, n0);
                     } else {
                         const uint32_t off = (uint32_t)(cta_rank * wrows) * ROW_BYTES;
-                        tma_load_2d_multicast(sa + 2 * A_BYTES + off, &map_w_hi, full, ks * BK, n0 + cta_rank * wrows, cl_mask);
-                        tma_load_2d_multicast(sa + 2 * A_BYTES + B_BYTES + off, &map_w_lo, full, ks * BK, n0 + cta_rank * wrows,
-                                              cl_mask);
+                        tma_load_2d_multicast(sw + off, &map_w_hi, full, ks * BK, n0 + cta_rank * wrows, cl_mask);
+                        tma_load_2d_multicast(sw + W_LO + off, &map_w_lo, full, ks * BK, n0 + cta_rank * wrows, cl_mask);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == LIN_W_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================================================= MMA issuer.  The whole warp runs the loop (so stage indices and
         // shared-memory descriptors stay in uniform registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
+        // Per K-slab: the two small cross terms (a_lo w_hi, a_hi w_lo), then the main product, then both ring slots are released;
+        // a partial sum (one TMEM buffer) covers DRAIN_SLABS_LINEAR slabs.
         {
             const bool leader = lane == 0;
             const uint32_t idesc = make_idesc(p.BN);
-            int stage = 0; uint32_t phase = 0;
+            int sa_i = 0; uint32_t pa = 0;
+            int sw_i = 0; uint32_t pw = 0;
             int acc = 0; uint32_t acc_phase = 0;
             int tm, tn;
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
                 for (int g = 0; g < num_groups; ++g) {
-                    // one partial sum = DRAIN_SLABS_LINEAR resident K-slabs; every small cross term (lo*hi, hi*lo) is issued before
-                    // the first main product, so only the main MMAs round at full magnitude
                     const int slabs = min(DRAIN_SLABS_LINEAR, num_k - g * DRAIN_SLABS_LINEAR);
                     mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);      // epilogue has drained this partial accumulator
                     const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-                    for (int j0 = 0; j0 < slabs; j0 += 2) {               // pairs of resident slabs: cross terms of both, then mains
-                        const int pair = min(2, slabs - j0);
-                        int st = stage; uint32_t ph = phase;
-                        for (int j = 0; j < pair; ++j) {
-                            mbar_wait(bar_full + 8 * st, ph);              // TMA bytes have landed
-                            if (++st == STAGES) { st = 0; ph ^= 1; }
-                        }
+                    for (int j = 0; j < slabs; ++j) {
+                        mbar_wait(bar_afull + 8 * sa_i, pa);               // TMA bytes have landed
+                        mbar_wait(bar_wfull + 8 * sw_i, pw);
                         tc_fence_after();
-                        st = stage;
-                        for (int j = 0; j < pair; ++j) {
-                            const uint32_t sa = smem_base + st * STAGE_BYTES;
-                            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
-                            const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
+                        const uint32_t sa = smem_base + sa_i * LIN_A_STAGE_BYTES;
+                        const uint32_t sw = ring_w + sw_i * LIN_W_STAGE_BYTES;
+                        const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
+                        const uint64_t w_hi = make_smem_desc(sw), w_lo = make_smem_desc(sw + W_LO);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) {         // UMMA K = 16 fp16 = 32 bytes = +2 in descriptor units
-                                const uint64_t adv = (uint64_t)(kk * 2);
-                                if (leader) umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (j0 | j | kk) != 0);
-                                if (leader) umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
-                            }
-                            if (++st == STAGES) st = 0;
+                        for (int kk = 0; kk < BK / 16; ++kk) {             // UMMA K = 16 fp16 = 32 bytes = +2 in descriptor units
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            if (leader) umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (j | kk) != 0);
+                            if (leader) umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                         }
-                        for (int j = 0; j < pair; ++j) {
-                            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                            const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) {
-                                const uint64_t adv = (uint64_t)(kk * 2);
-                                if (leader) umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
-                            }
-                            if (!leader) {} else if (CL == 1) umma_commit(bar_empty + 8 * stage);   // frees the smem slot when the MMAs retire
-                            else umma_commit_multicast(bar_empty + 8 * stage, cl_mask);   // ... in every CTA of the cluster
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        for (int kk = 0; kk < BK / 16; ++kk) {
+                            const uint64_t adv = (uint64_t)(kk * 2);
+                            if (leader) umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                         }
+                        if (leader) {
+                            umma_commit(bar_aempty + 8 * sa_i);                             // frees the slots when the MMAs retire
+                            if (CL == 1) umma_commit(bar_wempty + 8 * sw_i);
+                            else umma_commit_multicast(bar_wempty + 8 * sw_i, cl_mask);   // ... the weight slot in every CTA of the cluster
+                        }
+                        if (++sa_i == LIN_A_STAGES) { sa_i = 0; pa ^= 1; }
+                        if (++sw_i == LIN_W_STAGES) { sw_i = 0; pw ^= 1; }
                     }
                     if (leader) umma_commit(bar_tfull + 8 * acc);                      // partial sum complete -> drain
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -367,7 +393,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
                     for (int ch = 0; ch < HALF / 32; ++ch) {
                         const int col0 = n0 + 32 * ch;
-                        if (32 * ch + half * HALF >= p.BN || col0 >= p.N) continue;
+                        if (32 * ch + half * HALF >= p.BN || col0 >= p.N || col0 + 32 <= p.y_first_col) continue;
                         if (32 * ch + 32 + half * HALF > p.BN) {           // chunk straddles the tile's right edge (the columns
                             // beyond it belong to the next tile): a narrower, unswizzled [32][16 floats] chunk through its own map
                             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -461,7 +487,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                             for (int j = 0; j < 16; ++j) if (col0 + j < p.N) v[j] += rp[j];
                         }
                     }
-                    if (p.y) {
+                    if (p.y && col0 + 16 > p.y_first_col) {
                         float* yp = p.y + row * p.ldy + col0;
                         if (vec_y && full16) {
 #pragma unroll
@@ -635,6 +661,13 @@ int sm_count() {
 using namespace nfk;
 
 static bool pow2_exp_ok(int e) { return e >= -60 && e <= 60; }
+static int max_clusters_hint(int cl) { return nfk::tc::sm_count() / cl; }
+// bytes of one half (hi or lo) of a weight slot for the column tile the launch will use: BN rows x 64 bytes
+static int bn_rows_bytes(int out_features) {
+    int tiles = (out_features + nfk::tc::BN_MAX - 1) / nfk::tc::BN_MAX;
+    int bn = ((out_features + tiles - 1) / tiles + 15) / 16 * 16;
+    return bn * nfk::tc::ROW_BYTES;
+}
 
 extern "C" int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int relu, int32_t scale_exp, void* hi, void* lo,
                              int64_t ldo, int64_t n_rows, int32_t* flags, void* stream) {
@@ -658,8 +691,8 @@ extern "C" int nfk_linear_f16x3_supported(int64_t lda, int64_t ldw, int32_t in_f
 extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t lda, int32_t a_exp, const void* w_hi_,
                                 const void* w_lo_, int64_t ldw, int32_t w_exp, const float* bias, const float* R, int64_t ldr,
                                 float* Y, int64_t ldy, void* y_hi_, void* y_lo_, int64_t lds, int32_t y_exp, int32_t split_cols,
-                                int relu_out, int split_relu, int64_t n_rows, int32_t in_features, int32_t out_features,
-                                int32_t* flags, void* stream) {
+                                int32_t y_first_col, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
+                                int32_t out_features, int32_t* flags, void* stream) {
     const __half* a_hi = (const __half*)a_hi_; const __half* a_lo = (const __half*)a_lo_;
     const __half* w_hi = (const __half*)w_hi_; const __half* w_lo = (const __half*)w_lo_;
     __half* y_hi = (__half*)y_hi_; __half* y_lo = (__half*)y_lo_;
@@ -679,12 +712,17 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     p.split_n = split_cols > 0 ? split_cols : out_features;
     p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
     p.relu_out = relu_out; p.split_relu = split_relu;
+    p.y_first_col = y_first_col > 0 ? y_first_col : 0;
+    // the lo half of a weight slot starts at bn * 64 bytes: a multiple of 512 (the swizzle period) for bn a multiple of 8... of 16
+    p.w_slot_bytes = 2 * ((bn_rows_bytes(out_features) + 1023) / 1024 * 1024);
     p.num_n_tiles = (out_features + tc::BN_MAX - 1) / tc::BN_MAX;
     int bn = (out_features + p.num_n_tiles - 1) / p.num_n_tiles;
     bn = (bn + 15) / 16 * 16;
     p.BN = bn;
     p.num_n_tiles = (out_features + bn - 1) / bn;
     p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
+    p.a_stages = (tc::LIN_RING_BYTES - tc::LIN_W_STAGES * p.w_slot_bytes) / tc::LIN_A_STAGE_BYTES;
+    if (p.a_stages > tc::LIN_A_STAGES_MAX) p.a_stages = tc::LIN_A_STAGES_MAX;
 
     static int cluster_pref = 0;
     if (!cluster_pref) {
@@ -724,7 +762,14 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
         attr_once.mark(attr_dev);
     }
     const int units = (p.num_m_tiles + CL - 1) / CL;
-    p.n_inner = 0;   // measured r1: walking the column tiles of a row block back to back did not help
+    // a CTA walks the column tiles of its row block back to back: the activations are read from HBM once and re-read from L2
+    // (r1 measured no gain from this order -- its single 3-stage ring was bound by operand latency, not by DRAM traffic)
+    static int n_inner_pref = -1;
+    if (n_inner_pref < 0) {
+        const char* e = getenv("NFK_LINEAR_NINNER");
+        n_inner_pref = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.n_inner = (n_inner_pref && p.num_n_tiles > 1 && units >= max_clusters_hint(CL)) ? 1 : 0;
     const int work = units * p.num_n_tiles;
     const int max_clusters = tc::sm_count() / CL;
     cudaLaunchConfig_t cfg = {};

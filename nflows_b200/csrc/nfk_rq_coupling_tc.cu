@@ -342,7 +342,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                 // ---- spline on the FPT features held in registers, all features advanced together (ILP = FPT)
                 {
                     float yy[FPT], ll[FPT];
-                    rqs_eval_multi<NB, TAILS, FPT, MP>(p.sp, p.inverse != 0, xin, sum, yy, ll, flag);
+                    if (p.inverse) rqs_eval_lean<NB, TAILS, true, FPT, MP>(p.sp, xin, sum, yy, ll, flag);
+                    else rqs_eval_lean<NB, TAILS, false, FPT, MP>(p.sp, xin, sum, yy, ll, flag);
                     if (p.pair_only) {
                         // the consumer of this coupling's output is a tensor-core layer: it reads the fp16 split pair, so that
                         // is all that is written (no fp32 y, no separate split pass).  One staging area (hi rows, then lo

@@ -100,6 +100,10 @@ __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, 
     const bool pow2_rows = rows_per_group > 1 && (d_t & (d_t - 1)) == 0 && d_t <= 32;   // a row = an aligned lane group
     const bool use_prefetch = KMAX <= 16 && (kRowsThreads * M + 3) / 4 <= kMaxPrefetch * kRowsThreads;
     int flag = 0;
+    // element index -> (row in group, feature): shifts when the feature counts are powers of two (integer division is ~20
+    // instructions, and this kernel is issue-bound: ncu r2, 71 % issue-slot utilisation at 48 % of DRAM bandwidth)
+    const int sh_t = (d_t & (d_t - 1)) == 0 ? 31 - __clz(d_t) : -1;
+    const int sh_id = (d_id > 0 && (d_id & (d_id - 1)) == 0) ? 31 - __clz(d_id) : -1;
 
     float4 pre[kMaxPrefetch];
     // chunk (g, e0): elements [e0, e0 + cnt) of row group g
@@ -160,26 +164,46 @@ __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, 
         float ll = 0.0f;
         if (tid < cnt) {
             const int e = e0 + tid;
-            const int r = e / d_t;
+            const int r = sh_t >= 0 ? e >> sh_t : e / d_t;
             const int j = e - r * d_t;
-            const int col = t_cols ? t_cols[j] : j;
+            const int col = t_cols ? __ldg(t_cols + j) : j;
             const int64_t row = row0 + r;
             const float* q = sp + tid * M;
-            float w[KMAX], h[KMAX], d[KMAX + 1];
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                w[k] = (k < K) ? q[k] : 0.0f;
-                h[k] = (k < K) ? q[K + k] : 0.0f;
-            }
-            if (p.linear_tails) {
-#pragma unroll
-                for (int k = 0; k <= KMAX; ++k) d[k] = (k >= 1 && k < K) ? q[2 * K + k - 1] : p.edge_ud;
-            } else {
-#pragma unroll
-                for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? q[2 * K + k] : 0.0f;
-            }
             float yy;
-            rqs_eval<KMAX, EXACT>(p, inverse != 0, x[row * ldx + col], w, h, d, yy, ll, flag);
+            if (EXACT) {
+                // compile-time bin count: the lean form (binary bin search, template direction) straight on the staged parameters
+                constexpr int MPL = 3 * KMAX + 1;
+                float v[1 * MPL];
+                const float xin[1] = {x[row * ldx + col]};
+                float y1[1], l1[1];
+                if (p.linear_tails) {
+#pragma unroll
+                    for (int k = 0; k < 3 * KMAX - 1; ++k) v[k] = q[k];
+                    if (inverse) rqs_eval_lean<KMAX, true, true, 1, MPL>(p, xin, v, y1, l1, flag);
+                    else rqs_eval_lean<KMAX, true, false, 1, MPL>(p, xin, v, y1, l1, flag);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3 * KMAX + 1; ++k) v[k] = q[k];
+                    if (inverse) rqs_eval_lean<KMAX, false, true, 1, MPL>(p, xin, v, y1, l1, flag);
+                    else rqs_eval_lean<KMAX, false, false, 1, MPL>(p, xin, v, y1, l1, flag);
+                }
+                yy = y1[0]; ll = l1[0];
+            } else {
+                float w[KMAX], h[KMAX], d[KMAX + 1];
+#pragma unroll
+                for (int k = 0; k < KMAX; ++k) {
+                    w[k] = (k < K) ? q[k] : 0.0f;
+                    h[k] = (k < K) ? q[K + k] : 0.0f;
+                }
+                if (p.linear_tails) {
+#pragma unroll
+                    for (int k = 0; k <= KMAX; ++k) d[k] = (k >= 1 && k < K) ? q[2 * K + k - 1] : p.edge_ud;
+                } else {
+#pragma unroll
+                    for (int k = 0; k <= KMAX; ++k) d[k] = (k <= K) ? q[2 * K + k] : 0.0f;
+                }
+                rqs_eval<KMAX, EXACT>(p, inverse != 0, x[row * ldx + col], w, h, d, yy, ll, flag);
+            }
             y[row * ldy + col] = yy;
         }
 
@@ -199,9 +223,9 @@ __global__ void __launch_bounds__(kRowsThreads) rqs_rows_kernel(SplineParams p, 
         if (group_done) {
             // identity columns: bit-exact copy (coupling.py:96-97)
             for (int e = tid; e < rows_here * d_id; e += kRowsThreads) {
-                const int r = e / d_id;
-                const int col = id_cols[e - r * d_id];
-                y[(row0 + r) * ldy + col] = x[(row0 + r) * ldx + col];
+                const int r = sh_id >= 0 ? e >> sh_id : e / d_id;
+                const int col = __ldg(id_cols + (e - r * d_id));
+                y[(row0 + r) * ldy + col] = __ldcs(x + (row0 + r) * ldx + col);
             }
             if (lad_accum) {
                 if (rows_per_group == 1) {

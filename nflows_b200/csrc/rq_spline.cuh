@@ -63,13 +63,32 @@ NFK_HD float ex2_approx(float x) {
 #define NFK_SPLINE_FAST 1
 #endif
 
+NFK_HD float rcp_approx(float x) {                 // MUFU.RCP (<= 1 ulp), no range fix-ups
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+NFK_HD float lg2_approx(float x) {                 // MUFU.LG2
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return log2f(x);
+#endif
+}
+
+// a / b for operands far from the fp32 range limits (bin widths, interpolation denominators): one MUFU + one FMUL.
+// (__fdividef wraps the same two instructions in ~10 more that rescale huge denominators; ncu r2: the spline epilogue is
+// bound by instruction issue, 12 instructions per division.)
 NFK_HD float fast_div(float a, float b) {
 #if NFK_SPLINE_FAST
-#ifdef __CUDA_ARCH__
-    return __fdividef(a, b);                       // MUFU.RCP + FMUL
-#else
-    return a * (1.0f / b);
-#endif
+    return a * rcp_approx(b);
 #else
     return a / b;
 #endif
@@ -77,11 +96,7 @@ NFK_HD float fast_div(float a, float b) {
 
 NFK_HD float fast_log(float x) {
 #if NFK_SPLINE_FAST
-#ifdef __CUDA_ARCH__
-    return __logf(x);                              // MUFU.LG2 + FMUL
-#else
-    return log2f(x) * 0.693147180559945f;
-#endif
+    return lg2_approx(x) * 0.693147180559945f;     // __logf without its denormal rescaling: arguments here are >= ~1e-12
 #else
     return logf(x);
 #endif
@@ -200,6 +215,136 @@ NFK_HD void rqs_eval(const SplineParams& p, bool inverse, float x_in, const floa
     const bool identity = p.linear_tails && !inside;
     y = identity ? x_in : ys;
     lad = identity ? 0.0f : (inverse ? -l : l);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Lean evaluation of F features at once, IN PLACE on registers v[f*MP + 0..M): [NB widths | NB heights | NB-1 (tails) or NB+1
+// derivative logits] -- the form the tensor-core epilogues and (F = 1) the HBM-bound row kernel use when the bin count is a
+// compile-time constant.  Same formulas as rqs_eval; what is different is the instruction count (ncu r2: the spline was 624
+// instructions per feature and the coupling-step kernel's epilogue warps, not its tensor pipe, set the pace):
+//   * direction and tail mode are template parameters (no runtime selects between the forward and inverse formulas);
+//   * softmax arguments are one FFMA each (v * c - max * c);
+//   * all knots are formed first, then the bin is found by BINARY search over the register arrays -- log2(K) comparisons, each
+//     followed by selects that halve the candidate knots / derivative logits -- instead of a K-step scan carrying five selects;
+//   * divisions and logarithms are single MUFU operations (fast_div / fast_log above).
+// The f-loops are innermost so the F dependency chains interleave in the instruction stream.
+template <int NB, bool TAILS, bool INVERSE, int F, int MP>
+NFK_HD void rqs_eval_lean(const SplineParams& p, const float (&xin)[F], float (&v)[F * MP], float (&y)[F], float (&lad)[F],
+                          int& flag) {
+    constexpr int P = NB <= 2 ? 2 : NB <= 4 ? 4 : NB <= 8 ? 8 : NB <= 16 ? 16 : NB <= 32 ? 32 : 64;   // search width
+    bool inside[F];
+    float x[F], mw[F], mh[F], sw[F], sh[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        inside[f] = (xin[f] >= p.left) && (xin[f] <= p.right);   // NaN -> outside (reference :26-39)
+        if (!TAILS && !inside[f]) flag |= 1;                     // reference raises InputOutsideDomain (:81-82)
+        x[f] = inside[f] ? xin[f] : (xin[f] > p.right ? p.right : p.left);
+        mw[f] = v[f * MP];
+        mh[f] = v[f * MP + NB];
+    }
+#pragma unroll
+    for (int k = 1; k < NB; ++k)
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            mw[f] = fmaxf(mw[f], v[f * MP + k]);
+            mh[f] = fmaxf(mh[f], v[f * MP + NB + k]);
+        }
+    const float c2 = p.pre_scale * 1.4426950408889634f;          // log2(e) / sqrt(H)
+#pragma unroll
+    for (int f = 0; f < F; ++f) { mw[f] = -mw[f] * c2; mh[f] = -mh[f] * c2; sw[f] = 0.0f; sh[f] = 0.0f; }
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const float a = ex2_approx(fmaf(v[f * MP + k], c2, mw[f]));
+            const float b = ex2_approx(fmaf(v[f * MP + NB + k], c2, mh[f]));
+            v[f * MP + k] = a;
+            v[f * MP + NB + k] = b;
+            sw[f] += a;
+            sh[f] += b;
+        }
+    // knots: prefix sums of the mixed bin sizes, mapped to [left, right] / [bottom, top], first and last forced (:91-98, :106-113)
+    float kw[F][P + 1], kh[F][P + 1], dd[F][P + 1];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        sw[f] = p.mix_w * rcp_approx(sw[f]);                     // from here on: the softmax normalisers
+        sh[f] = p.mix_h * rcp_approx(sh[f]);
+        mw[f] = 0.0f; mh[f] = 0.0f;                              // ... and the running sums
+        kw[f][0] = p.left; kh[f][0] = p.bottom;
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            mw[f] += fmaf(v[f * MP + k], sw[f], p.min_w);
+            mh[f] += fmaf(v[f * MP + NB + k], sh[f], p.min_h);
+            kw[f][k + 1] = (k == NB - 1) ? p.right : fmaf(p.span_w, mw[f], p.left);
+            kh[f][k + 1] = (k == NB - 1) ? p.top : fmaf(p.span_h, mh[f], p.bottom);
+        }
+#pragma unroll
+    for (int k = 0; k <= P; ++k)
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            if (k > NB) { kw[f][k] = INFINITY; kh[f][k] = INFINITY; }           // padding of the search: never taken
+            // padded search (K not a power of two): the last real knot is compared at an inner level, where x == last knot
+            // must still fall into the last bin -- the searched array carries +inf there and gets the constant back below
+            if (P != NB && k == NB) { if (INVERSE) kh[f][k] = INFINITY; else kw[f][k] = INFINITY; }
+            // derivative logit at knot k: the boundary constant for linear tails, else the stored K+1 values
+            dd[f][k] = k > NB ? 0.0f : (TAILS ? ((k == 0 || k == NB) ? p.edge_ud : v[f * MP + 2 * NB + k - 1]) : v[f * MP + 2 * NB + k]);
+        }
+    // binary search for the last knot <= x (x is inside [first, last] knot by now): halve the candidates log2(P) times
+#pragma unroll
+    for (int width = P; width > 1; width >>= 1) {
+        const int h = width >> 1;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const bool up = x[f] >= (INVERSE ? kh[f][h] : kw[f][h]);
+#pragma unroll
+            for (int i = 0; i <= h; ++i) {
+                kw[f][i] = up ? kw[f][h + i] : kw[f][i];
+                kh[f][i] = up ? kh[f][h + i] : kh[f][i];
+                dd[f][i] = up ? dd[f][h + i] : dd[f][i];
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        if (P != NB) {
+            if (INVERSE) kh[f][1] = kh[f][1] == INFINITY ? p.top : kh[f][1];
+            else kw[f][1] = kw[f][1] == INFINITY ? p.right : kw[f][1];
+        }
+        const float b_cw = kw[f][0], b_w = kw[f][1] - kw[f][0];
+        const float b_ch = kh[f][0], b_h = kh[f][1] - kh[f][0];
+        const float d0 = p.min_d + fast_softplus(dd[f][0], p.beta, p.inv_beta);
+        const float d1 = p.min_d + fast_softplus(dd[f][1], p.beta, p.inv_beta);
+        const float delta = fast_div(b_h, b_w);
+        const float s = d0 + d1 - 2.0f * delta;
+        float theta, ys;
+        if (INVERSE) {
+            const float u = x[f] - b_ch;
+            const float a = u * s + b_h * (delta - d0);
+            const float b = b_h * d0 - u * s;
+            const float c = -delta * u;
+            const float disc = b * b - 4.0f * a * c;
+            if (!(disc >= 0.0f)) flag |= 2;                   // reference: assert (discriminant >= 0).all() (:142)
+            theta = fast_div(2.0f * c, -b - sqrtf(disc));
+            ys = theta * b_w + b_cw;
+        } else {
+            theta = fast_div(x[f] - b_cw, b_w);
+        }
+        const float t1mt = theta * (1.0f - theta);
+        const float den = delta + s * t1mt;
+        if (!INVERSE) {
+            const float num = b_h * (delta * (theta * theta) + d0 * t1mt);
+            ys = b_ch + fast_div(num, den);
+        }
+        const float omt = 1.0f - theta;
+        const float dnum = (delta * delta) * (d1 * (theta * theta) + 2.0f * delta * t1mt + d0 * (omt * omt));
+        const float l = fast_log(dnum) - 2.0f * fast_log(den);
+        const bool identity = TAILS && !inside[f];
+        y[f] = identity ? xin[f] : ys;
+        lad[f] = identity ? 0.0f : (INVERSE ? -l : l);
+    }
 }
 
 }  // namespace nfk

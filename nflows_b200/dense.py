@@ -290,10 +290,11 @@ def run_last(chain, state, r0, r1, use_tc, flags=None):
     return K.linear(state.raw[r0:r1], weight.detach(), b, relu_in=relu_in, relu_out=relu_out)
 
 
-def affine_map(x, weight, bias, x_pair=None, pair_cols=0, flags=None):
+def affine_map(x, weight, bias, x_pair=None, pair_cols=0, flags=None, y_first_col=0):
     """y = x @ weight.T + bias for a folded ActNorm/Permutation/LU run: one tensor-core GEMM.  x_pair: Pair16 of x when the
     producer already wrote it (else one split pass).  pair_cols > 0: also return the Pair16 of y, filled for its first
-    pair_cols columns (what the coupling behind this run feeds to its conditioner).  Returns (y, pair or None)."""
+    pair_cols columns (what the coupling behind this run feeds to its conditioner).  y_first_col > 0: nobody reads the fp32
+    values of the columns before it (the consumer multiplies their pair), so they are not written.  Returns (y, pair or None)."""
     from . import config
     n, k = x.shape
     if backend() == "tc" and k % 8 == 0 and K.f16x3_supported(k, weight.stride(0), k):
@@ -307,7 +308,8 @@ def affine_map(x, weight, bias, x_pair=None, pair_cols=0, flags=None):
         for r0 in range(0, n, step):
             r1 = min(n, r0 + step)
             K.linear_f16x3(x_pair.rows(r0, r1), w_pair, bias, want_y=True, y_out=y[r0:r1], want_split=y_pair is not None,
-                           split_cols=pair_cols, pair_out=None if y_pair is None else y_pair.rows(r0, r1), flags=flags)
+                           split_cols=pair_cols, pair_out=None if y_pair is None else y_pair.rows(r0, r1), flags=flags,
+                           y_first_col=y_first_col if y_pair is not None else 0)
         return y, y_pair
     return K.linear(x, weight, bias), None
 

@@ -174,16 +174,49 @@ class Float16RangeError(RuntimeError):
 
 def raise_for_flags(flags):
     """Mirror the reference's exceptions (rational_quadratic.py:81-82, :142).  One device->host read."""
+    raise_for_flag_value(int(flags.item()))
+
+
+def raise_for_flag_value(v):
     from .transforms.base import InputOutsideDomain
-    v = int(flags.item())
     if v & 1:
         raise InputOutsideDomain()
     if v & 2:
         raise AssertionError("rational-quadratic spline inverse: negative discriminant")
     if v & 4:
         raise Float16RangeError("an activation exceeded the fp16 split range of the tensor-core dense layers "
-                                "(|value| * 2^config.activation_exp > 65000): lower nflows_b200.config.activation_exp or set "
-                                "NFLOWS_B200_GEMM=simt")
+                                "(|value| * 2^config.activation_exp > 65000) and config.auto_activation_exp is off or exhausted: "
+                                "lower nflows_b200.config.activation_exp or set NFLOWS_B200_GEMM=simt")
+
+
+_warned_rescale = [False]
+
+
+def run_with_activation_rescale(fn):
+    """fn() -> (outputs, lad, flags): runs it, reads the flag word (config.check_domain) and, when a value left the fp16 split
+    range, runs it again with a smaller power-of-two scale for the activation pairs (config.auto_activation_exp) -- an input
+    magnitude the reference accepts must not raise here.  Other flags raise the reference's exceptions."""
+    from . import config
+    saved = config.activation_exp
+    try:
+        while True:
+            out, lad, flags = fn()
+            if not config.check_domain:
+                return out, lad
+            v = int(flags.item())
+            if (v & 4) and config.auto_activation_exp and config.activation_exp > -24:
+                config.activation_exp = max(-24, config.activation_exp - 5)      # results of this attempt are discarded
+                if not _warned_rescale[0]:
+                    _warned_rescale[0] = True
+                    import warnings
+                    warnings.warn("nflows_b200: an activation left the fp16 split range at activation_exp=%d; the call is "
+                                  "repeated with smaller exponents (set config.activation_exp lower to avoid the repeat)" % saved,
+                                  RuntimeWarning, stacklevel=4)
+                continue
+            raise_for_flag_value(v)
+            return out, lad
+    finally:
+        config.activation_exp = saved
 
 
 # ---- split-fp16 tensor-core dense layers ------------------------------------------------------------------------------
@@ -245,9 +278,10 @@ def f16x3_supported(lda, ldw, in_features):
 
 
 def linear_f16x3(a, w, bias=None, residual=None, relu_out=False, want_y=True, want_split=False, split_relu=False,
-                 split_exp=None, split_cols=0, y_out=None, pair_out=None, flags=None):
+                 split_exp=None, split_cols=0, y_out=None, pair_out=None, flags=None, y_first_col=0):
     """tcgen05 dense layer on Pair16 operands.  Returns (y or None, Pair16 or None); y_out / pair_out are caller-provided
-    destinations (row slices of larger buffers).  The pair output covers the first split_cols columns (0 = all)."""
+    destinations (row slices of larger buffers).  The pair output covers the first split_cols columns (0 = all); y_first_col > 0:
+    the fp32 result is only needed from that column on (the columns before it may stay unwritten)."""
     n, k = a.shape
     o = w.shape[0]
     dev = a.hi.device
@@ -264,8 +298,8 @@ def linear_f16x3(a, w, bias=None, residual=None, relu_out=False, want_y=True, wa
             a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, w.hi.data_ptr(), w.lo.data_ptr(), w.hi.stride(0), w.exp,
             N.ptr(bias), N.ptr(residual), residual.stride(0) if residual is not None else 0, N.ptr(y),
             y.stride(0) if y is not None else 0, pair.hi.data_ptr() if pair else 0, pair.lo.data_ptr() if pair else 0,
-            pair.hi.stride(0) if pair else 0, pair.exp if pair else 0, int(split_cols), int(relu_out), int(split_relu), n, k, o,
-            N.ptr(flags), N.stream()))
+            pair.hi.stride(0) if pair else 0, pair.exp if pair else 0, int(split_cols), int(y_first_col), int(relu_out),
+            int(split_relu), n, k, o, N.ptr(flags), N.stream()))
     return y, pair
 
 

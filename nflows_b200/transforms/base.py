@@ -63,11 +63,13 @@ class Transform(nn.Module):
         if torch.is_tensor(inputs) and self._native_ready(inputs, context):
             with K.on_device_of(inputs):
                 x = inputs if inputs.stride(-1) == 1 else inputs.contiguous()
-                lad = K.zeros_lad(x)
-                flags = K.new_flags(x.device)
-                out = self._native_apply(x, lad, flags, inverse, context)
-                if config.check_domain:
-                    K.raise_for_flags(flags)
+
+                def attempt():
+                    lad = K.zeros_lad(x)
+                    flags = K.new_flags(x.device)
+                    return self._native_apply(x, lad, flags, inverse, context), lad, flags
+
+                out, lad = K.run_with_activation_rescale(attempt)
             return out, lad
         K.warn_eager_cuda(inputs)
         return self._eager(inputs, context, inverse)
@@ -139,7 +141,18 @@ class CompositeTransform(Transform):
                 run = AffineRun.cached(self._affine_cache, leaves[i:j], x.device)
                 out_layout = wanted(j)
                 pair_cols = leaves[j][0].num_identity_features if out_layout is not None else 0
-                x, pair = run.apply(x, lad, layout, out_layout, x_pair=carry["pair"], pair_cols=pair_cols, flags=flags)
+                # the fp32 values of the identity block are never read when the coupling behind this run hands ONLY the fp16 pair
+                # of its output to another folded affine run (coupling._native_packed: pair_only) -- then they are not written
+                y_first_col = 0
+                if out_layout is not None and config.fused_pair_only and pair_cols % 8 == 0:
+                    k, lu_next = j + 1, False
+                    while k < len(leaves) and is_affine_leaf(leaves[k][0], x):
+                        lu_next = lu_next or leaves[k][0].__class__.__name__ in ("LULinear",)
+                        k += 1
+                    if lu_next:
+                        y_first_col = pair_cols
+                x, pair = run.apply(x, lad, layout, out_layout, x_pair=carry["pair"], pair_cols=pair_cols, flags=flags,
+                                    y_first_col=y_first_col)
                 carry["pair"] = pair
                 layout, owned = out_layout, True
                 i = j

@@ -133,10 +133,10 @@ class AffineRun:
             cache[key] = hit
         return hit[1]
 
-    def apply(self, x, lad, in_layout=None, out_layout=None, x_pair=None, pair_cols=0, flags=None):
-        """Returns (y, Pair16 of y's first pair_cols columns or None)."""
+    def apply(self, x, lad, in_layout=None, out_layout=None, x_pair=None, pair_cols=0, flags=None, y_first_col=0):
+        """Returns (y, Pair16 of y's first pair_cols columns or None).  y_first_col: see dense.affine_map."""
         weight, bias = self.operands(in_layout, out_layout)
-        y, y_pair = D.affine_map(x, weight, bias, x_pair=x_pair, pair_cols=pair_cols, flags=flags)
+        y, y_pair = D.affine_map(x, weight, bias, x_pair=x_pair, pair_cols=pair_cols, flags=flags, y_first_col=y_first_col)
         if self.lad_const != 0.0:
             K.add_const_(lad, self.lad_const)
         return y, y_pair

@@ -256,5 +256,78 @@ def main():
     save("ar_rq_small", dict(sd=ar.state_dict(), x=x, y=y, lad=lad, xinv=xi, ladinv=li))
 
 
+def next_rows():
+    """Round 2: reference outputs for the SURVEY section 8 'next' rows that were only compared with this package's own CPU path
+    in round 1 -- OneByOneConvolution on an image batch, PiecewiseRationalQuadraticCDF (both tail modes), an RQ coupling with
+    apply_unconditional_transform, SimpleRealNVP, and an MLP-conditioned RQ coupling.  Weights travel as reference state_dicts."""
+    from nflows.flows.realnvp import SimpleRealNVP
+    from nflows.nn.nets import MLP
+    rec = {}
+    with torch.no_grad():
+        torch.manual_seed(10)
+        conv = T.OneByOneConvolution(3, identity_init=False).eval()
+        x = torch.randn(10, 3, 28, 28)
+        y, lad = conv(x)
+        xi, li = conv.inverse(x)
+        rec["conv1x1"] = dict(sd=conv.state_dict(), x=x, y=y, lad=lad, xinv=xi, ladinv=li)
+        torch.manual_seed(11)
+        conv = T.OneByOneConvolution(12, identity_init=False).eval()
+        x = torch.randn(5, 12, 6, 6)
+        y, lad = conv(x)
+        rec["conv1x1_c12"] = dict(sd=conv.state_dict(), x=x, y=y, lad=lad)
+        for tails in (None, "linear"):
+            torch.manual_seed(12)
+            cdf = T.PiecewiseRationalQuadraticCDF(shape=[7], num_bins=6, tails=tails, tail_bound=2.0).eval()
+            for p_ in cdf.parameters():
+                p_.copy_(torch.randn(p_.shape) * 1.5)
+            x = torch.rand(300, 7) if tails is None else torch.randn(300, 7) * 1.5
+            y, lad = cdf(x)
+            xi, li = cdf.inverse(x if tails == "linear" else y)
+            rec["rq_cdf_%s" % (tails or "none")] = dict(sd=cdf.state_dict(), x=x, y=y, lad=lad, inv_in=(x if tails == "linear" else y),
+                                                        xinv=xi, ladinv=li)
+        torch.manual_seed(13)
+        t = T.PiecewiseRationalQuadraticCouplingTransform(
+            torchutils.create_alternating_binary_mask(16), lambda i, o: ResidualNet(i, o, hidden_features=32, num_blocks=1),
+            num_bins=8, tails="linear", tail_bound=3.0, apply_unconditional_transform=True).eval()
+        for name, p_ in t.named_parameters():
+            if "final_layer" in name or "unnormalized" in name:
+                p_.copy_(p_ * 3.0 + 0.3 * torch.randn(p_.shape))
+        x = torch.randn(200, 16) * 1.2
+        y, lad = t(x)
+        xi, li = t.inverse(x)
+        rec["rq_coupling_unconditional"] = dict(sd=t.state_dict(), x=x, y=y, lad=lad, xinv=xi, ladinv=li)
+        torch.manual_seed(14)
+        flow = SimpleRealNVP(features=10, hidden_features=16, num_layers=3, num_blocks_per_layer=2).eval()
+        for p_ in flow.parameters():
+            p_.add_(0.05 * torch.randn(p_.shape))
+        x = torch.randn(257, 10)
+        rec["simple_realnvp"] = dict(sd=flow.state_dict(), x=x, log_prob=flow.log_prob(x))
+        torch.manual_seed(15)
+        class CtxMLP(torch.nn.Module):        # the reference's MLP takes no context argument: the usual user-side adapter
+            def __init__(self, i, o):
+                super().__init__()
+                self.mlp = MLP([i], [o], [64, 64, 64])
+
+            def forward(self, inputs, context=None):
+                return self.mlp(inputs)
+
+        t = T.PiecewiseRationalQuadraticCouplingTransform(
+            torchutils.create_alternating_binary_mask(32), lambda i, o: CtxMLP(i, o),
+            num_bins=8, tails="linear", tail_bound=3.0).eval()
+        for name, p_ in t.named_parameters():
+            if "_final_layer" in name:
+                p_.mul_(3.0)
+        x = torch.randn(500, 32) * 1.2
+        y, lad = t(x)
+        xi, li = t.inverse(x)
+        yd, ladd = t.double()(x.double())
+        rec["rq_coupling_mlp"] = dict(sd=t.float().state_dict(), x=x, y=y, lad=lad, xinv=xi, ladinv=li, y_fp64=yd, lad_fp64=ladd)
+    save("next_rows", rec)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "next_rows":
+        next_rows()
+    else:
+        main()
+        next_rows()

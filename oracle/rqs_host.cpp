@@ -48,3 +48,42 @@ extern "C" int rqs_host_eval(const NfkSplineDesc* desc, int inverse, const float
     if (flags) *flags = flag;
     return 0;
 }
+
+// The lean multi-feature form (rqs_eval_lean): F = 2 features per call, parameters packed as the kernels hold them.
+template <int NB, bool TAILS, bool INV>
+static void lean_run(const nfk::SplineParams& p, const float* x, const float* uw, const float* uh, const float* ud, long long n,
+                     float* y, float* lad, int& flag) {
+    constexpr int M = TAILS ? 3 * NB - 1 : 3 * NB + 1;
+    constexpr int MP = (M + 7) / 8 * 8;
+    constexpr int ND = TAILS ? NB - 1 : NB + 1;
+    for (long long e = 0; e < n; e += 2) {
+        float v[2 * MP] = {0};
+        float xin[2] = {0, 0}, yy[2], ll[2];
+        for (int f = 0; f < 2 && e + f < n; ++f) {
+            xin[f] = x[e + f];
+            for (int k = 0; k < NB; ++k) { v[f * MP + k] = uw[(e + f) * NB + k]; v[f * MP + NB + k] = uh[(e + f) * NB + k]; }
+            for (int k = 0; k < ND; ++k) v[f * MP + 2 * NB + k] = ud[(e + f) * ND + k];
+        }
+        int fl = 0;
+        nfk::rqs_eval_lean<NB, TAILS, INV, 2, MP>(p, xin, v, yy, ll, fl);
+        for (int f = 0; f < 2 && e + f < n; ++f) { y[e + f] = yy[f]; lad[e + f] = ll[f]; }
+        if (e + 1 < n || true) flag |= fl;      // (the pad element of an odd tail is x = 0 with zero logits: inside, no flag)
+    }
+}
+
+extern "C" int rqs_host_eval_lean(const NfkSplineDesc* desc, int inverse, const float* x, const float* uw, const float* uh,
+                                  const float* ud, long long n, float* y, float* lad, int* flags) {
+    nfk::SplineParams p;
+    nfk::make_spline_params_host(desc, &p);
+    int flag = 0;
+#define LEAN(NB)                                                                                    \
+    if (p.num_bins == NB) {                                                                         \
+        if (p.linear_tails) { if (inverse) lean_run<NB, true, true>(p, x, uw, uh, ud, n, y, lad, flag); else lean_run<NB, true, false>(p, x, uw, uh, ud, n, y, lad, flag); } \
+        else { if (inverse) lean_run<NB, false, true>(p, x, uw, uh, ud, n, y, lad, flag); else lean_run<NB, false, false>(p, x, uw, uh, ud, n, y, lad, flag); } \
+        if (flags) *flags = flag;                                                                   \
+        return 0;                                                                                   \
+    }
+    LEAN(4) LEAN(8) LEAN(10) LEAN(16)
+#undef LEAN
+    return -1;
+}

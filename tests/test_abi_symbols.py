@@ -47,7 +47,7 @@ def test_argument_validation_happens_before_any_cuda_call():
     assert lib.nfk_linear_f16x3_supported(784, 784, 12) == 0           # K not a multiple of 8
     assert lib.nfk_linear_f16x3_supported(12, 784, 8) == 0             # row pitch not a multiple of 8 elements
     # no output requested
-    rc = lib.nfk_linear_f16x3(16, 16, 8, 6, 16, 16, 8, 10, 0, 0, 0, 0, 0, 0, 0, 0, 6, 0, 0, 0, 4, 8, 8, 0, 0)
+    rc = lib.nfk_linear_f16x3(16, 16, 8, 6, 16, 16, 8, 10, 0, 0, 0, 0, 0, 0, 0, 0, 6, 0, 0, 0, 0, 4, 8, 8, 0, 0)
     assert rc == -1 and b"no output" in lib.nfk_last_error()
     # y and the pair output are mutually exclusive in the fused kernel; both NULL is an error as well
     desc = _native.spline_desc(8, "linear", 3.0, 0, 1, 0, 1, 1e-3, 1e-3, 1e-3, False, 16.0)

@@ -137,3 +137,48 @@ def test_autoregressive_rq_cpu_seeded():
     ar2.load_state_dict(g2["sd"])
     xi, li = ar2.inverse(g2["x"])
     assert rel_err(xi, g2["xinv"]) <= TOL and rel_err(li, g2["ladinv"]) <= TOL
+
+
+@torch.no_grad()
+def test_next_rows_cpu_replay_of_reference_goldens():
+    """tests/golden/next_rows.pt (reference outputs, oracle/make_golden.py next_rows) through the package's CPU path: the
+    reference's state_dicts load with strict=True and the outputs agree."""
+    import warnings
+
+    from nflows_b200.flows import SimpleRealNVP
+    from nflows_b200.nn.nets import MLP, ResidualNet
+    from nflows_b200.utils import torchutils
+    g = load_golden("next_rows")
+    for key, channels in (("conv1x1", 3), ("conv1x1_c12", 12)):
+        r = g[key]
+        conv = T.OneByOneConvolution(channels, identity_init=False).eval()
+        conv.load_state_dict(r["sd"], strict=True)
+        y, lad = conv(r["x"])
+        assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= TOL
+    for tails in (None, "linear"):
+        r = g["rq_cdf_%s" % (tails or "none")]
+        cdf = T.PiecewiseRationalQuadraticCDF(shape=[7], num_bins=6, tails=tails, tail_bound=2.0).eval()
+        cdf.load_state_dict(r["sd"], strict=True)
+        y, lad = cdf(r["x"])
+        xi, li = cdf.inverse(r["inv_in"])
+        assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= TOL and rel_err(xi, r["xinv"]) <= TOL
+    r = g["rq_coupling_unconditional"]
+    t = T.PiecewiseRationalQuadraticCouplingTransform(
+        torchutils.create_alternating_binary_mask(16), lambda i, o: ResidualNet(i, o, hidden_features=32, num_blocks=1),
+        num_bins=8, tails="linear", tail_bound=3.0, apply_unconditional_transform=True).eval()
+    t.load_state_dict(r["sd"], strict=True)
+    y, lad = t(r["x"])
+    assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= TOL
+    r = g["simple_realnvp"]
+    flow = SimpleRealNVP(features=10, hidden_features=16, num_layers=3, num_blocks_per_layer=2).eval()
+    flow.load_state_dict(r["sd"], strict=True)
+    assert rel_err(flow.log_prob(r["x"]), r["log_prob"]) <= TOL
+    r = g["rq_coupling_mlp"]
+    t = T.PiecewiseRationalQuadraticCouplingTransform(
+        torchutils.create_alternating_binary_mask(32), lambda i, o: MLP([i], [o], [64, 64, 64]),
+        num_bins=8, tails="linear", tail_bound=3.0).eval()
+    t.load_state_dict({k.replace("transform_net.mlp.", "transform_net."): v for k, v in r["sd"].items()}, strict=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        y, lad = t(r["x"])
+    assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= TOL
