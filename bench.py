@@ -89,6 +89,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """Threads for the CPU arm: the cores this process may run on (not the box's logical CPU count: 128 threads on a 64-core
+    allowance ran the oracle 40x slower), capped at 64; NFLOWS_REF_THREADS overrides.  torchrun's OMP_NUM_THREADS=1 is undone."""
+    env = os.environ.get("NFLOWS_REF_THREADS")
+    if env:
+        return max(1, int(env))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(64, n))
+
+
 def build_flow(seed=0):
     from nflows_b200.flows import recipes
     torch.manual_seed(seed)
@@ -250,7 +263,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(host_threads())
     flow = build_flow()
     rates, rows_total = [], 0
     for i in range(args.warmup + args.steps):
@@ -436,7 +449,7 @@ def run_native(args):
                                                        "the same GPU" % (best[2], best[1])}
         except Exception as exc:     # a context figure only: never let it take the bench line down
             result["torch_cuda_baseline"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        torch.set_num_threads(host_threads())
         rate, sample_rows, threads = cpu_oracle_rate(flow.cpu(), budget_s=args.ref_budget, max_rows=args.ref_rows)
         result["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                                   "sample": "%d rows of the same workload in chunks of 2048" % sample_rows}

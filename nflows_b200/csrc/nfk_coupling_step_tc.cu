@@ -101,6 +101,8 @@ struct StepParams {
     float* y;
     const int32_t* t_cols;
     int t_col0, tma_y, pair_only;
+    int drain_f;                  // K-slabs accumulated in TMEM per partial sum of the final layer (DRAIN_SLABS_FUSED, or all)
+    int tma_x;                    // inputs of the transformed features arrive as TMA boxes (consecutive columns, 16-byte aligned)
     float out_scale;
     float* lad_accum;
     int32_t* flags;
@@ -124,7 +126,8 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         const __grid_constant__ CUtensorMap map_wf_hi, const __grid_constant__ CUtensorMap map_wf_lo,
                         const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yh,
                         const __grid_constant__ CUtensorMap map_yl, const __grid_constant__ CUtensorMap map_h_hi,
-                        const __grid_constant__ CUtensorMap map_h_lo, const StepParams p) {
+                        const __grid_constant__ CUtensorMap map_h_lo, const __grid_constant__ CUtensorMap map_x,
+                        const StepParams p) {
     using Cfg = StepCfg<NB, TAILS, EWG>;
     constexpr int MP = Cfg::MP, FPT = Cfg::FPT, HC = Cfg::HC, BN = Cfg::BN, TF = Cfg::TF;
     constexpr int NEPI = 4 * EWG;                  // epilogue warps
@@ -140,7 +143,11 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const uint32_t bar_aready = bars + 112;       // the epilogue warps have written the next layer's operand into R
     const uint32_t bar_outready = bars + 120;     // trunk_only: ... the trunk's output, ready for the TMA stores
     const uint32_t bar_bfull = bars + 128, bar_bempty = bars + 144;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STEP_BAR_OFF + 160);
+    const uint32_t bar_xfull = bars + 160, bar_xempty = bars + 176;      // the two TMA-staged input tiles (tma_x)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STEP_BAR_OFF + 200);
+    // [2][128 rows][TF] fp32 input tiles in the tail of the ring region, which the final layer's geometry (G2) leaves unused
+    constexpr int X_TILE_OFF = STEP_R_BYTES + STEP_G2_STAGES * STEP_G2_STAGE_BYTES;
+    static_assert(X_TILE_OFF + 2 * BM * 8 * 4 <= STEP_R_BYTES + STEP_RING_BYTES, "input tiles must fit behind the G2 stages");
     float* s_bias = reinterpret_cast<float*>(smem_gen + STEP_BIAS_OFF);        // [2][STEP_BN_MAX]
     float* s_lad = reinterpret_cast<float*>(smem_gen + STEP_X_OFF);            // [EWG-1][128], aliases the (then idle) x staging
 
@@ -151,7 +158,8 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const int num_kh = p.H / BK;                             // K-slabs of every other layer (H is a multiple of 32)
     const int groups0 = (num_k0 + DRAIN_SLABS_LINEAR - 1) / DRAIN_SLABS_LINEAR;
     const int groupsh = (num_kh + DRAIN_SLABS_LINEAR - 1) / DRAIN_SLABS_LINEAR;
-    const int groupsf = (num_kh + DRAIN_SLABS_FUSED - 1) / DRAIN_SLABS_FUSED;
+    const int drain_f = p.drain_f;                           // K-slabs per partial sum of the final layer
+    const int groupsf = (num_kh + drain_f - 1) / drain_f;
     const int nch = p.H > 128 ? 2 : 1;                       // column chunks of a square layer
     const int ch = p.H / nch;                                // columns per chunk (multiple of 16)
 
@@ -160,6 +168,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, NEPI); }
         mbar_init(bar_aready, NEPI); mbar_init(bar_outready, NEPI);
         for (int b = 0; b < 2; ++b) { mbar_init(bar_bfull + 8 * b, 1); mbar_init(bar_bempty + 8 * b, NEPI); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_xfull + 8 * b, 1); mbar_init(bar_xempty + 8 * b, NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w0_hi); prefetch_tmap(&map_w0_lo);
         prefetch_tmap(&map_wt_hi); prefetch_tmap(&map_wt_lo); prefetch_tmap(&map_wf_hi); prefetch_tmap(&map_wf_lo);
@@ -185,6 +194,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     for (int s = 0; s < STEP_NBAR; ++s) slot_wait(s);
                 };
                 int bslot = 0; uint32_t bphase = 0, out_phase = 0;
+                int xslot = 0; uint32_t xphase = 0;
                 for (int u = first; u < units; u += step) {
                     const int m0 = (u * CL + cta_rank) * BM;
                     // ---- G0: initial layer, A and W streamed through 48 KB stages laid over R
@@ -264,6 +274,13 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         constexpr int wrows = BN / CL;
                         int s = 0;
                         for (int n = 0; n < p.num_n_tiles; ++n) {
+                            if (p.tma_x) {   // this tile's inputs: box [128 rows][TF columns] of x (columns past d_t are zero-filled)
+                                mbar_wait(bar_xempty + 8 * xslot, xphase ^ 1);
+                                mbar_expect_tx(bar_xfull + 8 * xslot, (uint32_t)(BM * TF * 4));
+                                tma_load_2d(smem_base + X_TILE_OFF + xslot * (BM * TF * 4), &map_x, bar_xfull + 8 * xslot,
+                                            p.t_col0 + n * TF, m0);
+                                if (++xslot == 2) { xslot = 0; xphase ^= 1; }
+                            }
                             {   // this tile's slice of the packed bias -> s_bias[bslot]
                                 const int cols = min(BN, p.d_t * MP - n * BN);
                                 mbar_wait(bar_bempty + 8 * bslot, bphase ^ 1);
@@ -400,13 +417,13 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     int s = 0;
                     for (int n = 0; n < p.num_n_tiles; ++n) {
                         for (int g = 0; g < groupsf; ++g) {
-                            const int slabs = min(DRAIN_SLABS_FUSED, num_kh - g * DRAIN_SLABS_FUSED);
+                            const int slabs = min(drain_f, num_kh - g * drain_f);
                             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                             for (int j = 0; j < slabs; ++j) {
                                 full_wait(s);
                                 tc_fence_after();
-                                const uint32_t sa = smem_base + (g * DRAIN_SLABS_FUSED + j) * STEP_SLAB_BYTES;
+                                const uint32_t sa = smem_base + (g * drain_f + j) * STEP_SLAB_BYTES;
                                 const uint32_t sw = ring + s * STEP_G2_STAGE_BYTES;
                                 const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
                                 const uint64_t w_hi = make_smem_desc(sw), w_lo = make_smem_desc(sw + STEP_G2_LO_OFF);
@@ -442,6 +459,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
         int acc = 0; uint32_t acc_phase = 0;
         int flag = 0;
         int bslot = 0; uint32_t bphase = 0;
+        int xslot = 0; uint32_t xphase = 0;
         int ybuf = 0;
         float4* skip = p.skip_buf + (size_t)blockIdx.x * (size_t)(p.H / 4) * 128 + r_tile;       // [c4 * 128]: coalesced across lanes
         float* s_x = reinterpret_cast<float*>(smem_gen + STEP_X_OFF) + (tid_x - 128) * FPT;     // this thread's staged inputs
@@ -463,7 +481,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             };
-            if (!p.trunk_only) prefetch_x(0);
+            if (!p.trunk_only && !p.tma_x) prefetch_x(0);
             // ------------------------------------------------ conditioner trunk: layer l's epilogue writes layer l+1's operand into R
             for (int l = 0; l < p.num_layers; ++l) {
                 const int lf = p.layer_flags[l];
@@ -596,10 +614,20 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 }
                 // ---- this tile's inputs out of the staging slot, the next tile's on their way into it
                 float xin[FPT];
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (p.tma_x) {
+                    mbar_wait(bar_xfull + 8 * xslot, xphase);
+                    const float* xt = reinterpret_cast<const float*>(smem_gen + X_TILE_OFF + xslot * (BM * TF * 4)) + r_tile * TF + wg * FPT;
 #pragma unroll
-                for (int f = 0; f < FPT; ++f) xin[f] = (row_ok && j0 + f < p.d_t) ? s_x[f] : 0.0f;
-                if (n + 1 < p.num_n_tiles) prefetch_x(n + 1);
+                    for (int f = 0; f < FPT; ++f) xin[f] = (row_ok && j0 + f < p.d_t) ? xt[f] : 0.0f;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_xempty + 8 * xslot);
+                    if (++xslot == 2) { xslot = 0; xphase ^= 1; }
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+                    for (int f = 0; f < FPT; ++f) xin[f] = (row_ok && j0 + f < p.d_t) ? s_x[f] : 0.0f;
+                    if (n + 1 < p.num_n_tiles) prefetch_x(n + 1);
+                }
                 // ---- back from the accumulators' power-of-two scaled domain, plus the packed bias staged in shared memory
                 {
                     mbar_wait(bar_bfull + 8 * bslot, bphase);
@@ -631,14 +659,22 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         __half* sh = reinterpret_cast<__half*>(buf);
                         __half* sl = sh + BM * YROW16;
                         const int off = r_tile * YROW16 + (n % YG16) * TF + wg * FPT;
+                        __half hi[FPT], lo[FPT];
 #pragma unroll
                         for (int f = 0; f < FPT; ++f) {
-                            __half hi, lo;
                             int f2 = 0;
-                            split_f16(yy[f], p.out_scale, hi, lo, f2);
-                            sh[off + f] = hi;
-                            sl[off + f] = lo;
+                            split_f16(yy[f], p.out_scale, hi[f], lo[f], f2);
                             if (row_ok && j0 + f < p.d_t) { lad_row += ll[f]; flag |= f2; }
+                        }
+                        if (FPT % 2 == 0) {          // two features per 32-bit store (2-byte stores: 4 bank-conflict passes each)
+#pragma unroll
+                            for (int f = 0; f < FPT; f += 2) {
+                                *reinterpret_cast<__half2*>(sh + off + f) = __halves2half2(hi[f], hi[f + 1]);
+                                *reinterpret_cast<__half2*>(sl + off + f) = __halves2half2(lo[f], lo[f + 1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int f = 0; f < FPT; ++f) { sh[off + f] = hi[f]; sl[off + f] = lo[f]; }
                         }
                     } else {
                         float* dst = reinterpret_cast<float*>(buf) + r_tile * YROW + (n % YG) * TF + wg * FPT;
@@ -725,7 +761,7 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
         if ((rc = make_map(&mwt_lo, (const __half*)d->wt_lo, (int64_t)L * H, H, d->ldwt, ch / CL))) return rc;
     }
     mwf_hi = mw0_hi; mwf_lo = mw0_lo;
-    CUtensorMap my = mw0_hi, myh = mw0_hi, myl = mw0_hi, mh_hi = mw0_hi, mh_lo = mw0_hi;
+    CUtensorMap my = mw0_hi, myh = mw0_hi, myl = mw0_hi, mh_hi = mw0_hi, mh_lo = mw0_hi, mx = mw0_hi;
     if (p.trunk_only) {
         if ((rc = make_map(&mh_hi, (const __half*)d->h_hi, p.n_rows, H, d->ldh, BM))) return rc;
         if ((rc = make_map(&mh_lo, (const __half*)d->h_lo, p.n_rows, H, d->ldh, BM))) return rc;
@@ -735,6 +771,10 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
         if ((rc = make_map(&mwf_lo, (const __half*)d->wp_lo, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
         p.num_n_tiles = (p.d_t + Cfg::TF - 1) / Cfg::TF;
         p.tma_y = (p.y && !p.t_cols && p.t_col0 % 4 == 0 && p.ldy % 4 == 0 && aligned16(p.y)) ? 1 : 0;
+        // inputs as TMA boxes of TF columns: consecutive columns from a 16-byte aligned first column (tiles start at multiples of TF >= 4 floats...
+        // TF = 2: 8-byte boxes are below the TMA minimum -> cp.async staging)
+        p.tma_x = (!p.t_cols && Cfg::TF >= 4 && p.t_col0 % 4 == 0 && p.ldx % 4 == 0 && aligned16(p.x) && !getenv("NFK_STEP_NO_TMA_X")) ? 1 : 0;
+        if (p.tma_x && (rc = make_out_map(&mx, const_cast<float*>(p.x), p.n_rows, p.t_col0 + p.d_t, p.ldx, Cfg::TF, BM))) return rc;
         if (p.tma_y && (rc = make_out_map(&my, p.y, p.n_rows, p.t_col0 + p.d_t, p.ldy, Cfg::YROW, BM))) return rc;
         if (p.pair_only) {
             NFK_REQUIRE(!p.t_cols && p.t_col0 % 8 == 0 && d->lds % 8 == 0 && aligned16(d->y_hi) && aligned16(d->y_lo),
@@ -769,8 +809,8 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = (CL == 2) ? cudaLaunchKernelEx(&cfg, kern2, ma_hi, ma_lo, mw0_hi, mw0_lo, mwt_hi, mwt_lo, mwf_hi, mwf_lo, my, myh, myl, mh_hi, mh_lo, p)
-                  : cudaLaunchKernelEx(&cfg, kern1, ma_hi, ma_lo, mw0_hi, mw0_lo, mwt_hi, mwt_lo, mwf_hi, mwf_lo, my, myh, myl, mh_hi, mh_lo, p);
+    e = (CL == 2) ? cudaLaunchKernelEx(&cfg, kern2, ma_hi, ma_lo, mw0_hi, mw0_lo, mwt_hi, mwt_lo, mwf_hi, mwf_lo, my, myh, myl, mh_hi, mh_lo, mx, p)
+                  : cudaLaunchKernelEx(&cfg, kern1, ma_hi, ma_lo, mw0_hi, mw0_lo, mwt_hi, mwt_lo, mwf_hi, mwf_lo, my, myh, myl, mh_hi, mh_lo, mx, p);
     if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(rq_coupling_step_kernel, cluster %d): %s", CL, cudaGetErrorString(e));
     return check_launch("rq_coupling_step_kernel");
 }
@@ -821,6 +861,7 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
     NFK_REQUIRE(d->n_rows < (1ll << 31), "n_rows too large for one launch");
     tc::StepParams p;
     memset(&p, 0, sizeof(p));
+    p.drain_f = tc::DRAIN_SLABS_FUSED;
     p.bias_trunk = d->bias_trunk; p.skip_buf = (float4*)d->workspace; p.H = d->hidden_features; p.K0 = d->in_features;
     p.num_layers = 1 + d->num_square_layers; p.act_scale = ldexpf(1.0f, d->act_exp); p.trunk_only = trunk_only ? 1 : 0;
     for (int l = 0; l < p.num_layers; ++l) {
@@ -851,6 +892,15 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
     p.ldx = d->ldx; p.ldy = d->ldy; p.d_t = d->d_t; p.inverse = d->inverse;
     p.inv_acc_scale_f = ldexpf(1.0f, -(d->act_exp + d->wp_exp));
     p.pair_only = d->y_hi ? 1 : 0; p.out_scale = ldexpf(1.0f, d->y_exp);
+    {
+        static int drain_pref = 0;
+        if (!drain_pref) {
+            const char* e = getenv("NFK_STEP_DRAIN");
+            drain_pref = e ? atoi(e) : tc::DRAIN_SLABS_FUSED;
+            if (drain_pref < 1) drain_pref = tc::DRAIN_SLABS_FUSED;
+        }
+        p.drain_f = drain_pref;
+    }
     const bool tails = d->spline->linear_tails != 0;
     // four epilogue warpgroups where a column tile has at least four features, else two
 #define NFK_STEP(NB)                                                                                                       \

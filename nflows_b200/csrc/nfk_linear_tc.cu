@@ -67,7 +67,7 @@ struct Params {
     int n_inner;             // tile schedule, see tile_of()
     int tma_store;           // outputs are TMA-addressable (16-byte aligned bases and row pitches): staged stores
     int y_first_col;         // the fp32 result is only needed for columns >= y_first_col (32-column chunks below it are skipped)
-    int a_stages;            // A ring depth
+    int a_stages, w_stages;  // ring depths
     int w_slot_bytes;        // bytes per W ring slot (hi part first, lo part at w_slot_bytes / 2)
 };
 
@@ -75,7 +75,7 @@ struct Params {
 // 64 bytes each, twice), the rest A slots of 16 KB [A hi | A lo] (BN = 208: 3 x 26 KB + 5 x 16 KB; BN = 256: 3 x 32 KB + 4 x 16 KB)
 constexpr int LIN_RING_BYTES = 160 * 1024;
 constexpr int LIN_A_STAGES_MAX = 8;
-constexpr int LIN_W_STAGES = 3;
+constexpr int LIN_W_STAGES_MAX = 8;
 constexpr int LIN_A_STAGE_BYTES = 2 * A_BYTES;
 constexpr int LIN_BAR_OFF = LIN_RING_BYTES;
 constexpr int LIN_STG_OFF = LIN_BAR_OFF + 1024;                         // after the rings and the barrier block, 1024-aligned
@@ -111,7 +111,13 @@ __device__ __forceinline__ bool tile_of(const int it, const int n_inner, const i
     return t < units * num_n;
 }
 
-template <int CL>
+// PAIR (with CL = 2): the two CTAs of a cluster form a tcgen05 CTA PAIR (cta_group::2).  ONE 256 x BN x 16 MMA, issued by the
+// leader (cluster rank 0), drives both SMs' tensor cores: each CTA supplies its own 128 A rows and HALF of the weight tile from
+// its own shared memory.  Per SM that halves the weight bytes written by TMA and read by the MMA -- the multicast form moves
+// A + the FULL weight tile through every SM's 128 B/clk shared-memory port (ncu r2: 43 % tensor pipe at ~100 B/clk of operand
+// traffic).  Every TMA load of either CTA counts its bytes on the LEADER's "full" barrier; the leader's tcgen05.commit releases
+// ring slots and accumulators in both CTAs; the epilogue warps of both CTAs report drained accumulators to the leader.
+template <int CL, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -122,26 +128,29 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const int LIN_A_STAGES = p.a_stages;
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+    const int LIN_A_STAGES = p.a_stages, LIN_W_STAGES = p.w_stages;
     const uint32_t LIN_W_STAGE_BYTES = (uint32_t)p.w_slot_bytes, W_LO = LIN_W_STAGE_BYTES / 2;
     const uint32_t ring_w = smem_base + LIN_A_STAGES * LIN_A_STAGE_BYTES;
     const uint32_t bars = smem_base + LIN_BAR_OFF;                         // 8-byte mbarriers
     const uint32_t bar_afull = bars, bar_aempty = bars + 8 * LIN_A_STAGES_MAX;
-    const uint32_t bar_wfull = bars + 16 * LIN_A_STAGES_MAX, bar_wempty = bar_wfull + 8 * LIN_W_STAGES;
-    const uint32_t bar_tfull = bar_wempty + 8 * LIN_W_STAGES, bar_tempty = bar_tfull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + LIN_BAR_OFF + 16 * LIN_A_STAGES_MAX + 16 * LIN_W_STAGES + 32);
+    const uint32_t bar_wfull = bars + 16 * LIN_A_STAGES_MAX, bar_wempty = bar_wfull + 8 * LIN_W_STAGES_MAX;
+    const uint32_t bar_tfull = bar_wempty + 8 * LIN_W_STAGES_MAX, bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + LIN_BAR_OFF + 16 * LIN_A_STAGES_MAX + 16 * LIN_W_STAGES_MAX + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = (p.K + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < LIN_A_STAGES; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 1); }
-        for (int s = 0; s < LIN_W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, CL); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+        // multicast form: both CTAs' MMA threads release a weight slot (the peer multicasts into it); pair form: the leader's
+        // commit reaches both CTAs' barriers
+        for (int s = 0; s < LIN_W_STAGES; ++s) { mbar_init(bar_wfull + 8 * s, 1); mbar_init(bar_wempty + 8 * s, PAIR ? 1 : CL); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, PAIR ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 1) { if (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), 512); else tmem_alloc(smem_u32(tmem_slot), 512); }
     tc_fence_before();
     if (CL > 1) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
@@ -163,9 +172,16 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     mbar_wait(bar_aempty + 8 * stage, phase ^ 1);
                     const uint32_t full = bar_afull + 8 * stage;
                     const uint32_t sa = smem_base + stage * LIN_A_STAGE_BYTES;
-                    mbar_expect_tx(full, 2u * A_BYTES);
-                    tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
-                    tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
+                    if (PAIR) {                                            // both CTAs' rows are counted on the leader's barrier
+                        const uint32_t lead = mapa_rank(full, 0);
+                        if (cta_rank == 0) mbar_expect_tx(full, 4u * A_BYTES);
+                        tma_load_2d_pair(sa, &map_a_hi, lead, ks * BK, m0);
+                        tma_load_2d_pair(sa + A_BYTES, &map_a_lo, lead, ks * BK, m0);
+                    } else {
+                        mbar_expect_tx(full, 2u * A_BYTES);
+                        tma_load_2d(sa, &map_a_hi, full, ks * BK, m0);
+                        tma_load_2d(sa + A_BYTES, &map_a_lo, full, ks * BK, m0);
+                    }
                     if (++stage == LIN_A_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -184,6 +200,14 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     mbar_wait(bar_wempty + 8 * stage, phase ^ 1);          // every CTA of the cluster has released the slot
                     const uint32_t full = bar_wfull + 8 * stage;
                     const uint32_t sw = ring_w + stage * LIN_W_STAGE_BYTES;
+                    if (PAIR) {                  // this CTA's half of the tile's weight rows, at the slot base of its own shared memory
+                        const uint32_t lead = mapa_rank(full, 0);
+                        if (cta_rank == 0) mbar_expect_tx(full, tx_bytes);
+                        tma_load_2d_pair(sw, &map_w_hi, lead, ks * BK, n0 + cta_rank * wrows);
+                        tma_load_2d_pair(sw + W_LO, &map_w_lo, lead, ks * BK, n0 + cta_rank * wrows);
+                        if (++stage == LIN_W_STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(full, tx_bytes);
                     if (CL == 1) {
                         tma_load_2d(sw, &map_w_hi, full, ks * BK, n0);
@@ -197,14 +221,18 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
         // ================================================= MMA issuer.  The whole warp runs the loop (so stage indices and
         // shared-memory descriptors stay in uniform registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
         // Per K-slab: the two small cross terms (a_lo w_hi, a_hi w_lo), then the main product, then both ring slots are released;
         // a partial sum (one TMEM buffer) covers DRAIN_SLABS_LINEAR slabs.
         {
             const bool leader = lane == 0;
-            const uint32_t idesc = make_idesc(p.BN);
+            const uint32_t idesc = make_idesc(p.BN, PAIR ? 2 * BM : BM);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
+                if (!leader) return;
+                if (PAIR) umma_f16_pair(d, a, b, idesc, accumulate); else umma_f16(d, a, b, idesc, accumulate);
+            };
             int sa_i = 0; uint32_t pa = 0;
             int sw_i = 0; uint32_t pw = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -212,7 +240,8 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
                 for (int g = 0; g < num_groups; ++g) {
                     const int slabs = min(DRAIN_SLABS_LINEAR, num_k - g * DRAIN_SLABS_LINEAR);
-                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);      // epilogue has drained this partial accumulator
+                    if (PAIR) mbar_wait_cluster(bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
+                    else mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this partial accumulator
                     const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                     for (int j = 0; j < slabs; ++j) {
                         mbar_wait(bar_afull + 8 * sa_i, pa);               // TMA bytes have landed
@@ -225,23 +254,30 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk) {             // UMMA K = 16 fp16 = 32 bytes = +2 in descriptor units
                             const uint64_t adv = (uint64_t)(kk * 2);
-                            if (leader) umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, (j | kk) != 0);
-                            if (leader) umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                            mma(d_tmem, a_lo + adv, w_hi + adv, (j | kk) != 0);
+                            mma(d_tmem, a_hi + adv, w_lo + adv, 1);
                         }
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk) {
                             const uint64_t adv = (uint64_t)(kk * 2);
-                            if (leader) umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                            mma(d_tmem, a_hi + adv, w_hi + adv, 1);
                         }
                         if (leader) {
-                            umma_commit(bar_aempty + 8 * sa_i);                             // frees the slots when the MMAs retire
-                            if (CL == 1) umma_commit(bar_wempty + 8 * sw_i);
-                            else umma_commit_multicast(bar_wempty + 8 * sw_i, cl_mask);   // ... the weight slot in every CTA of the cluster
+                            if (PAIR) {                                                     // both CTAs' slots, when the MMAs retire
+                                umma_commit_pair(bar_aempty + 8 * sa_i, cl_mask);
+                                umma_commit_pair(bar_wempty + 8 * sw_i, cl_mask);
+                            } else {
+                                umma_commit(bar_aempty + 8 * sa_i);                         // frees the slots when the MMAs retire
+                                if (CL == 1) umma_commit(bar_wempty + 8 * sw_i);
+                                else umma_commit_multicast(bar_wempty + 8 * sw_i, cl_mask);   // ... the weight slot in every CTA of the cluster
+                            }
                         }
                         if (++sa_i == LIN_A_STAGES) { sa_i = 0; pa ^= 1; }
                         if (++sw_i == LIN_W_STAGES) { sw_i = 0; pw ^= 1; }
                     }
-                    if (leader) umma_commit(bar_tfull + 8 * acc);                      // partial sum complete -> drain
+                    if (leader) {                                                       // partial sum complete -> drain
+                        if (PAIR) umma_commit_pair(bar_tfull + 8 * acc, cl_mask); else umma_commit(bar_tfull + 8 * acc);
+                    }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
@@ -347,7 +383,10 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(mapa_rank(bar_tempty + 8 * acc, 0));   // the leader's MMA thread reuses the accumulator
+                    else mbar_arrive(bar_tempty + 8 * acc);
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
             if (p.tma_store) {
@@ -527,7 +566,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
 
     tc_fence_before();
     if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA exits while a peer may still signal its barriers
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) { if (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------- fp32 -> fp16 (hi, lo) split pair, optional relu
@@ -713,23 +752,28 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
     p.relu_out = relu_out; p.split_relu = split_relu;
     p.y_first_col = y_first_col > 0 ? y_first_col : 0;
-    // the lo half of a weight slot starts at bn * 64 bytes: a multiple of 512 (the swizzle period) for bn a multiple of 8... of 16
-    p.w_slot_bytes = 2 * ((bn_rows_bytes(out_features) + 1023) / 1024 * 1024);
     p.num_n_tiles = (out_features + tc::BN_MAX - 1) / tc::BN_MAX;
     int bn = (out_features + p.num_n_tiles - 1) / p.num_n_tiles;
     bn = (bn + 15) / 16 * 16;
     p.BN = bn;
     p.num_n_tiles = (out_features + bn - 1) / bn;
     p.num_m_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
-    p.a_stages = (tc::LIN_RING_BYTES - tc::LIN_W_STAGES * p.w_slot_bytes) / tc::LIN_A_STAGE_BYTES;
-    if (p.a_stages > tc::LIN_A_STAGES_MAX) p.a_stages = tc::LIN_A_STAGES_MAX;
 
     static int cluster_pref = 0;
     if (!cluster_pref) {
         const char* e = getenv("NFK_CLUSTER");
-        cluster_pref = (e && e[0] == '1') ? 1 : 2;
+        cluster_pref = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2;
     }
-    const int CL = (cluster_pref == 2 && p.num_m_tiles >= 2) ? 2 : 1;
+    const int CL = (cluster_pref >= 2 && p.num_m_tiles >= 2) ? 2 : 1;
+    // CTA pairs (cta_group::2): UMMA M = 256 needs N a multiple of 16 and each CTA's half a multiple of 8 rows
+    const bool pair = CL == 2 && cluster_pref == 3;
+    // ring split: weight slots hold this CTA's rows of a K-slab (all BN rows, or BN / 2 in a pair), hi part then lo part, each
+    // rounded to the 1024-byte swizzle alignment; the rest of the ring holds 16 KB A slots
+    const int w_rows = pair ? bn / 2 : bn;
+    p.w_slot_bytes = 2 * ((w_rows * tc::ROW_BYTES + 1023) / 1024 * 1024);
+    p.w_stages = pair ? 4 : 3;
+    p.a_stages = (tc::LIN_RING_BYTES - p.w_stages * p.w_slot_bytes) / tc::LIN_A_STAGE_BYTES;
+    if (p.a_stages > tc::LIN_A_STAGES_MAX) p.a_stages = tc::LIN_A_STAGES_MAX;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     int rc;
     if ((rc = tc::make_map(&ma_hi, a_hi, n_rows, in_features, lda, tc::BM))) return rc;
@@ -755,9 +799,11 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     static DeviceOnce attr_once;
     int attr_dev = 0;
     if (attr_once.pending(&attr_dev)) {
-        cudaError_t e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
+            e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc::linear_f16x3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::LIN_SMEM_BYTES);
         if (e != cudaSuccess) return fail(NFK_E_CUDA, "cudaFuncSetAttribute(smem=%d): %s", tc::LIN_SMEM_BYTES, cudaGetErrorString(e));
         attr_once.mark(attr_dev);
     }
@@ -782,8 +828,9 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, myt, myht, mylt, p)
-                               : cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<1>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, myt, myht, mylt, p);
+    cudaError_t le = pair      ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2, true>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, myt, myht, mylt, p)
+                     : (CL == 2) ? cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<2, false>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, myt, myht, mylt, p)
+                                 : cudaLaunchKernelEx(&cfg, tc::linear_f16x3_kernel<1, false>, ma_hi, ma_lo, mw_hi, mw_lo, my, myh, myl, myt, myht, mylt, p);
     if (le != cudaSuccess) return fail(NFK_E_CUDA, "cudaLaunchKernelEx(linear_f16x3_kernel, cluster %d): %s", CL, cudaGetErrorString(le));
     return check_launch("linear_f16x3_kernel");
 }
