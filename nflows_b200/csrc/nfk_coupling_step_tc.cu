@@ -101,6 +101,7 @@ struct StepParams {
     float* y;
     const int32_t* t_cols;
     int t_col0, tma_y, pair_only;
+    int mma_warps;                // 2: two MMA-issuing warps take alternate partial sums; 1: one issuer
     int drain_f;                  // K-slabs accumulated in TMEM per partial sum of the final layer (DRAIN_SLABS_FUSED, or all)
     int tma_x;                    // inputs of the transformed features arrive as TMA boxes (consecutive columns, 16-byte aligned)
     float out_scale;
@@ -309,24 +310,38 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     }
                 }
             }
-        } else if (warp == 1) {
-            // ================================================= MMA issuer (whole warp runs the loop, lane 0 issues)
+        } else if (warp == 1 || (warp == 3 && p.mma_warps == 2)) {
+            // ================================================= MMA issuers (whole warp runs the loop, lane 0 issues).
+            // TWO issuing warps take alternate partial sums (warp 1: TMEM buffer 0, warp 3: buffer 1): what limited the tensor
+            // pipe was the issue sequence itself -- every tcgen05.mma is preceded by an ELECT and five R2UR moves of its
+            // descriptors into uniform registers, ~190 cycles per instruction against 96 cycles of tensor work at N = 192 (ncu r2:
+            // the issuing warp never waited on a barrier, tensor pipe 50 %).  The MMAs of one partial sum come from one warp, in
+            // program order, so results do not depend on how the two warps interleave.
             const bool leader = lane == 0;
+            const int my = warp == 1 ? 0 : 1;
+            const bool solo = p.mma_warps != 2;
             uint32_t seen = 0;                                       // bit s: parity of the number of fills of ring slot s consumed
             auto full_wait = [&](int s) { mbar_wait(bar_full + 8 * s, (seen >> s) & 1u); seen ^= 1u << s; };
             auto release = [&](int s) {
                 if (!leader) return;
                 if (CL == 1) umma_commit(bar_empty + 8 * s); else umma_commit_multicast(bar_empty + 8 * s, cl_mask);
             };
+            // the other warp's partial sum: step over its ring slots (slot parities stay in step with the barriers)
+            auto pass = [&](int& s, int count, int stages) {
+                for (int j = 0; j < count; ++j) { seen ^= 1u << s; if (++s == stages) s = 0; }
+            };
             const uint32_t idesc0 = make_idesc(p.H), idesc1 = make_idesc(ch), idescf = make_idesc(BN);
-            int acc = 0; uint32_t acc_phase = 0, aready_phase = 0;
+            uint32_t gc = 0;                                         // partial sums so far: buffer gc & 1, use (gc >> 1) of it
+            uint32_t aready_phase = 0;
             for (int u = first; u < units; u += step) {
                 // ---- initial layer: A and W from the G0 stages
                 {
                     int s = 0;
-                    for (int g = 0; g < groups0; ++g) {
+                    for (int g = 0; g < groups0; ++g, ++gc) {
                         const int slabs = min(DRAIN_SLABS_LINEAR, num_k0 - g * DRAIN_SLABS_LINEAR);
-                        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                        if (!solo && (int)(gc & 1u) != my) { pass(s, slabs, STEP_G0_STAGES); continue; }
+                        const int acc = gc & 1u;
+                        mbar_wait(bar_tempty + 8 * acc, ((gc >> 1) & 1u) ^ 1u);
                         const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                         int st = s;
                         for (int j = 0; j < slabs; ++j) { full_wait(st); if (++st == STEP_G0_STAGES) st = 0; }
@@ -356,7 +371,6 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                             if (++s == STEP_G0_STAGES) s = 0;
                         }
                         if (leader) umma_commit(bar_tfull + 8 * acc);
-                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     }
                 }
                 // ---- square layers: A from R, W from the G1 units
@@ -366,9 +380,11 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         mbar_wait(bar_aready, aready_phase);
                         aready_phase ^= 1;
                         tc_fence_after();
-                        for (int g = 0; g < groupsh; ++g) {
+                        for (int g = 0; g < groupsh; ++g, ++gc) {
                             const int slabs = min(DRAIN_SLABS_LINEAR, num_kh - g * DRAIN_SLABS_LINEAR);
-                            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                            if (!solo && (int)(gc & 1u) != my) { pass(s, slabs * nch, STEP_G1_UNITS); continue; }
+                            const int acc = gc & 1u;
+                            mbar_wait(bar_tempty + 8 * acc, ((gc >> 1) & 1u) ^ 1u);
                             for (int c = 0; c < nch; ++c) {
                                 const uint32_t d_tmem = tmem_base + acc * BN_MAX + c * ch;
                                 int st = s;
@@ -402,7 +418,6 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                                 }
                             }
                             if (leader) umma_commit(bar_tfull + 8 * acc);
-                            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         }
                     }
                 }
@@ -416,9 +431,11 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     tc_fence_after();
                     int s = 0;
                     for (int n = 0; n < p.num_n_tiles; ++n) {
-                        for (int g = 0; g < groupsf; ++g) {
+                        for (int g = 0; g < groupsf; ++g, ++gc) {
                             const int slabs = min(drain_f, num_kh - g * drain_f);
-                            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                            if (!solo && (int)(gc & 1u) != my) { pass(s, slabs, STEP_G2_STAGES); continue; }
+                            const int acc = gc & 1u;
+                            mbar_wait(bar_tempty + 8 * acc, ((gc >> 1) & 1u) ^ 1u);
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                             for (int j = 0; j < slabs; ++j) {
                                 full_wait(s);
@@ -442,7 +459,6 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                                 if (++s == STEP_G2_STAGES) s = 0;
                             }
                             if (leader) umma_commit(bar_tfull + 8 * acc);
-                            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                         }
                     }
                 }
@@ -862,6 +878,14 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
     tc::StepParams p;
     memset(&p, 0, sizeof(p));
     p.drain_f = tc::DRAIN_SLABS_FUSED;
+    {
+        static int mma_pref = 0;
+        if (!mma_pref) {
+            const char* e = getenv("NFK_STEP_MMA_WARPS");
+            mma_pref = (e && e[0] == '1') ? 1 : 2;
+        }
+        p.mma_warps = mma_pref;
+    }
     p.bias_trunk = d->bias_trunk; p.skip_buf = (float4*)d->workspace; p.H = d->hidden_features; p.K0 = d->in_features;
     p.num_layers = 1 + d->num_square_layers; p.act_scale = ldexpf(1.0f, d->act_exp); p.trunk_only = trunk_only ? 1 : 0;
     for (int l = 0; l < p.num_layers; ++l) {

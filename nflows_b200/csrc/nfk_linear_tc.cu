@@ -68,6 +68,7 @@ struct Params {
     int tma_store;           // outputs are TMA-addressable (16-byte aligned bases and row pitches): staged stores
     int y_first_col;         // the fp32 result is only needed for columns >= y_first_col (32-column chunks below it are skipped)
     int a_stages, w_stages;  // ring depths
+    int mma_warps;           // 2: two MMA-issuing warps take alternate partial sums
     int w_slot_bytes;        // bytes per W ring slot (hi part first, lo part at w_slot_bytes / 2)
 };
 
@@ -221,13 +222,17 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
             }
         }
-    } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
-        // ================================================= MMA issuer.  The whole warp runs the loop (so stage indices and
+    } else if ((warp == 1 || (warp == 3 && p.mma_warps == 2)) && (!PAIR || cta_rank == 0)) {
+        // ================================================= MMA issuers.  The whole warp runs the loop (so stage indices and
         // shared-memory descriptors stay in uniform registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
         // Per K-slab: the two small cross terms (a_lo w_hi, a_hi w_lo), then the main product, then both ring slots are released;
-        // a partial sum (one TMEM buffer) covers DRAIN_SLABS_LINEAR slabs.
+        // a partial sum (one TMEM buffer) covers DRAIN_SLABS_LINEAR slabs.  TWO issuing warps take alternate partial sums (warp 1:
+        // buffer 0, warp 3: buffer 1): every tcgen05.mma costs the issuing thread ~190 cycles of ELECT / R2UR operand moves
+        // against ~100 cycles of tensor work, so one issuer left the tensor pipe half idle (ncu r2).
         {
             const bool leader = lane == 0;
+            const int my = warp == 1 ? 0 : 1;
+            const bool solo = p.mma_warps != 2;
             const uint32_t idesc = make_idesc(p.BN, PAIR ? 2 * BM : BM);
             auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accumulate) {
                 if (!leader) return;
@@ -235,11 +240,20 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             };
             int sa_i = 0; uint32_t pa = 0;
             int sw_i = 0; uint32_t pw = 0;
-            int acc = 0; uint32_t acc_phase = 0;
+            uint32_t gc = 0;                                              // partial sums so far: buffer gc & 1, use gc >> 1 of it
             int tm, tn;
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
-                for (int g = 0; g < num_groups; ++g) {
+                for (int g = 0; g < num_groups; ++g, ++gc) {
                     const int slabs = min(DRAIN_SLABS_LINEAR, num_k - g * DRAIN_SLABS_LINEAR);
+                    if (!solo && (int)(gc & 1u) != my) {                  // the other issuer's partial sum: step over its slots
+                        for (int j = 0; j < slabs; ++j) {
+                            if (++sa_i == LIN_A_STAGES) { sa_i = 0; pa ^= 1; }
+                            if (++sw_i == LIN_W_STAGES) { sw_i = 0; pw ^= 1; }
+                        }
+                        continue;
+                    }
+                    const int acc = gc & 1u;
+                    const uint32_t acc_phase = (gc >> 1) & 1u;
                     if (PAIR) mbar_wait_cluster(bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
                     else mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this partial accumulator
                     const uint32_t d_tmem = tmem_base + acc * BN_MAX;
@@ -278,7 +292,6 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     if (leader) {                                                       // partial sum complete -> drain
                         if (PAIR) umma_commit_pair(bar_tfull + 8 * acc, cl_mask); else umma_commit(bar_tfull + 8 * acc);
                     }
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
             }
         }
@@ -752,6 +765,14 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
     p.relu_out = relu_out; p.split_relu = split_relu;
     p.y_first_col = y_first_col > 0 ? y_first_col : 0;
+    {
+        static int mma_pref = 0;
+        if (!mma_pref) {
+            const char* e = getenv("NFK_LINEAR_MMA_WARPS");
+            mma_pref = (e && e[0] == '1') ? 1 : 2;
+        }
+        p.mma_warps = mma_pref;
+    }
     p.num_n_tiles = (out_features + tc::BN_MAX - 1) / tc::BN_MAX;
     int bn = (out_features + p.num_n_tiles - 1) / p.num_n_tiles;
     bn = (bn + 15) / 16 * 16;

@@ -480,8 +480,13 @@ def test_next_rows_against_reference_goldens(cuda_device):
         l64 = l64.sum(dim=1)
         assert rel_err(got.cpu(), r["y"]) <= TOL, tails
         assert rel_err(gl.cpu(), l64) <= max(3e-5, 3 * rel_err(r["lad"], l64)), tails
+        # the inverse on these sharp bins amplifies round-off: the reference's own fp32 inverse is 4e-4 .. 5e-4 from fp64 -> sandwich
         back, bl = cdf.inverse(r["inv_in"].to(cuda_device))
-        assert rel_err(back.cpu(), r["xinv"]) <= 1e-4 and rel_err(bl.cpu(), r["ladinv"]) <= 1e-4, tails
+        x64, li64 = spline(r["inv_in"].double(), ex(sd["unnormalized_widths"]), ex(sd["unnormalized_heights"]),
+                           ex(sd["unnormalized_derivatives"]), inverse=True, **kw)
+        li64 = li64.sum(dim=1)
+        assert rel_err(back.cpu(), x64) <= max(1e-4, 3 * rel_err(r["xinv"], x64)), tails
+        assert rel_err(bl.cpu(), li64) <= max(1e-4, 3 * rel_err(r["ladinv"], li64)), tails
 
     r = g["rq_coupling_unconditional"]
     t = T.PiecewiseRationalQuadraticCouplingTransform(
