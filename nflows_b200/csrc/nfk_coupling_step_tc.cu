@@ -102,6 +102,7 @@ struct StepParams {
     const int32_t* t_cols;
     int t_col0, tma_y, pair_only;
     int mma_warps;                // 2: two MMA-issuing warps take alternate partial sums; 1: one issuer
+    int drain_t;                  // K-slabs accumulated in TMEM per partial sum of a trunk layer (DRAIN_SLABS_LINEAR by default)
     int drain_f;                  // K-slabs accumulated in TMEM per partial sum of the final layer (DRAIN_SLABS_FUSED, or all)
     int tma_x;                    // inputs of the transformed features arrive as TMA boxes (consecutive columns, 16-byte aligned)
     float out_scale;
@@ -157,8 +158,9 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     const int warp = tid_x >> 5, lane = tid_x & 31;
     const int num_k0 = (p.K0 + BK - 1) / BK;                 // K-slabs of the initial layer
     const int num_kh = p.H / BK;                             // K-slabs of every other layer (H is a multiple of 32)
-    const int groups0 = (num_k0 + DRAIN_SLABS_LINEAR - 1) / DRAIN_SLABS_LINEAR;
-    const int groupsh = (num_kh + DRAIN_SLABS_LINEAR - 1) / DRAIN_SLABS_LINEAR;
+    const int drain_t = p.drain_t;                           // K-slabs per partial sum of a trunk layer
+    const int groups0 = (num_k0 + drain_t - 1) / drain_t;
+    const int groupsh = (num_kh + drain_t - 1) / drain_t;
     const int drain_f = p.drain_f;                           // K-slabs per partial sum of the final layer
     const int groupsf = (num_kh + drain_f - 1) / drain_f;
     const int nch = p.H > 128 ? 2 : 1;                       // column chunks of a square layer
@@ -231,10 +233,10 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         int s = 0;
                         for (int l = 1; l < p.num_layers; ++l) {
                             for (int g = 0; g < groupsh; ++g) {
-                                const int slabs = min(DRAIN_SLABS_LINEAR, num_kh - g * DRAIN_SLABS_LINEAR);
+                                const int slabs = min(drain_t, num_kh - g * drain_t);
                                 for (int c = 0; c < nch; ++c) {
                                     for (int j = 0; j < slabs; ++j) {
-                                        const int ks = g * DRAIN_SLABS_LINEAR + j;
+                                        const int ks = g * drain_t + j;
                                         const int row0 = (l - 1) * p.H + c * ch;
                                         slot_wait(s);
                                         const uint32_t full = bar_full + 8 * s;
@@ -338,17 +340,15 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 {
                     int s = 0;
                     for (int g = 0; g < groups0; ++g, ++gc) {
-                        const int slabs = min(DRAIN_SLABS_LINEAR, num_k0 - g * DRAIN_SLABS_LINEAR);
+                        const int slabs = min(drain_t, num_k0 - g * drain_t);
                         if (!solo && (int)(gc & 1u) != my) { pass(s, slabs, STEP_G0_STAGES); continue; }
                         const int acc = gc & 1u;
                         mbar_wait(bar_tempty + 8 * acc, ((gc >> 1) & 1u) ^ 1u);
                         const uint32_t d_tmem = tmem_base + acc * BN_MAX;
-                        int st = s;
-                        for (int j = 0; j < slabs; ++j) { full_wait(st); if (++st == STEP_G0_STAGES) st = 0; }
-                        tc_fence_after();
-                        st = s;
-                        for (int j = 0; j < slabs; ++j) {              // cross terms of the group first (small magnitudes)
-                            const uint32_t sa = smem_base + st * STAGE_BYTES;
+                        for (int j = 0; j < slabs; ++j) {              // per slab: the two small cross terms, the main product, release
+                            full_wait(s);
+                            tc_fence_after();
+                            const uint32_t sa = smem_base + s * STAGE_BYTES;
                             const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
                             const uint64_t w_hi = make_smem_desc(sa + 2 * A_BYTES), w_lo = make_smem_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
@@ -357,11 +357,6 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                                 if (leader) umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc0, (j | kk) != 0);
                                 if (leader) umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc0, 1);
                             }
-                            if (++st == STEP_G0_STAGES) st = 0;
-                        }
-                        for (int j = 0; j < slabs; ++j) {              // then the main products; each releases its stage
-                            const uint32_t sa = smem_base + s * STAGE_BYTES;
-                            const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sa + 2 * A_BYTES);
 #pragma unroll
                             for (int kk = 0; kk < BK / 16; ++kk) {
                                 const uint64_t adv = (uint64_t)(kk * 2);
@@ -381,19 +376,17 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         aready_phase ^= 1;
                         tc_fence_after();
                         for (int g = 0; g < groupsh; ++g, ++gc) {
-                            const int slabs = min(DRAIN_SLABS_LINEAR, num_kh - g * DRAIN_SLABS_LINEAR);
+                            const int slabs = min(drain_t, num_kh - g * drain_t);
                             if (!solo && (int)(gc & 1u) != my) { pass(s, slabs * nch, STEP_G1_UNITS); continue; }
                             const int acc = gc & 1u;
                             mbar_wait(bar_tempty + 8 * acc, ((gc >> 1) & 1u) ^ 1u);
                             for (int c = 0; c < nch; ++c) {
                                 const uint32_t d_tmem = tmem_base + acc * BN_MAX + c * ch;
-                                int st = s;
-                                for (int j = 0; j < slabs; ++j) { full_wait(st); if (++st == STEP_G1_UNITS) st = 0; }
-                                tc_fence_after();
-                                st = s;
                                 for (int j = 0; j < slabs; ++j) {
-                                    const uint32_t sa = smem_base + (g * DRAIN_SLABS_LINEAR + j) * STEP_SLAB_BYTES;
-                                    const uint32_t sw = ring + st * STEP_G1_UNIT_BYTES;
+                                    full_wait(s);
+                                    tc_fence_after();
+                                    const uint32_t sa = smem_base + (g * drain_t + j) * STEP_SLAB_BYTES;
+                                    const uint32_t sw = ring + s * STEP_G1_UNIT_BYTES;
                                     const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_BYTES);
                                     const uint64_t w_hi = make_smem_desc(sw), w_lo = make_smem_desc(sw + STEP_G1_LO_OFF);
 #pragma unroll
@@ -402,12 +395,6 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                                         if (leader) umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc1, (j | kk) != 0);
                                         if (leader) umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc1, 1);
                                     }
-                                    if (++st == STEP_G1_UNITS) st = 0;
-                                }
-                                for (int j = 0; j < slabs; ++j) {
-                                    const uint32_t sa = smem_base + (g * DRAIN_SLABS_LINEAR + j) * STEP_SLAB_BYTES;
-                                    const uint32_t sw = ring + s * STEP_G1_UNIT_BYTES;
-                                    const uint64_t a_hi = make_smem_desc(sa), w_hi = make_smem_desc(sw);
 #pragma unroll
                                     for (int kk = 0; kk < BK / 16; ++kk) {
                                         const uint64_t adv = (uint64_t)(kk * 2);
@@ -879,12 +866,16 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
     memset(&p, 0, sizeof(p));
     p.drain_f = tc::DRAIN_SLABS_FUSED;
     {
-        static int mma_pref = 0;
+        static int mma_pref = 0, drain_t_pref = 0;
         if (!mma_pref) {
             const char* e = getenv("NFK_STEP_MMA_WARPS");
-            mma_pref = (e && e[0] == '1') ? 1 : 2;
+            mma_pref = (e && e[0] == '2') ? 2 : 1;
+            const char* t = getenv("NFK_STEP_TRUNK_DRAIN");
+            drain_t_pref = t ? atoi(t) : tc::DRAIN_SLABS_LINEAR;
+            if (drain_t_pref < 1) drain_t_pref = tc::DRAIN_SLABS_LINEAR;
         }
         p.mma_warps = mma_pref;
+        p.drain_t = drain_t_pref;
     }
     p.bias_trunk = d->bias_trunk; p.skip_buf = (float4*)d->workspace; p.H = d->hidden_features; p.K0 = d->in_features;
     p.num_layers = 1 + d->num_square_layers; p.act_scale = ldexpf(1.0f, d->act_exp); p.trunk_only = trunk_only ? 1 : 0;

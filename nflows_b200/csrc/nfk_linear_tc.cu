@@ -69,6 +69,7 @@ struct Params {
     int y_first_col;         // the fp32 result is only needed for columns >= y_first_col (32-column chunks below it are skipped)
     int a_stages, w_stages;  // ring depths
     int mma_warps;           // 2: two MMA-issuing warps take alternate partial sums
+    int drain;               // K-slabs accumulated in TMEM per partial sum (DRAIN_SLABS_LINEAR by default)
     int w_slot_bytes;        // bytes per W ring slot (hi part first, lo part at w_slot_bytes / 2)
 };
 
@@ -158,7 +159,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     const int cta_rank = CL > 1 ? (int)cluster_ctarank() : 0;
     constexpr uint16_t cl_mask = (uint16_t)((1u << CL) - 1);
-    const int num_groups = (num_k + DRAIN_SLABS_LINEAR - 1) / DRAIN_SLABS_LINEAR;     // partial sums per tile
+    const int num_groups = (num_k + p.drain - 1) / p.drain;               // partial sums per tile
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");     // hand registers to the epilogue warpgroups
@@ -244,7 +245,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             int tm, tn;
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
                 for (int g = 0; g < num_groups; ++g, ++gc) {
-                    const int slabs = min(DRAIN_SLABS_LINEAR, num_k - g * DRAIN_SLABS_LINEAR);
+                    const int slabs = min(p.drain, num_k - g * p.drain);
                     if (!solo && (int)(gc & 1u) != my) {                  // the other issuer's partial sum: step over its slots
                         for (int j = 0; j < slabs; ++j) {
                             if (++sa_i == LIN_A_STAGES) { sa_i = 0; pa ^= 1; }
@@ -766,12 +767,16 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     p.relu_out = relu_out; p.split_relu = split_relu;
     p.y_first_col = y_first_col > 0 ? y_first_col : 0;
     {
-        static int mma_pref = 0;
+        static int mma_pref = 0, drain_pref = 0;
         if (!mma_pref) {
             const char* e = getenv("NFK_LINEAR_MMA_WARPS");
-            mma_pref = (e && e[0] == '1') ? 1 : 2;
+            mma_pref = (e && e[0] == '2') ? 2 : 1;
+            const char* d = getenv("NFK_LINEAR_DRAIN");
+            drain_pref = d ? atoi(d) : tc::DRAIN_SLABS_LINEAR;
+            if (drain_pref < 1) drain_pref = tc::DRAIN_SLABS_LINEAR;
         }
         p.mma_warps = mma_pref;
+        p.drain = drain_pref;
     }
     p.num_n_tiles = (out_features + tc::BN_MAX - 1) / tc::BN_MAX;
     int bn = (out_features + p.num_n_tiles - 1) / p.num_n_tiles;

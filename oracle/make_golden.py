@@ -325,9 +325,41 @@ def next_rows():
     save("next_rows", rec)
 
 
+def context_rows():
+    """Round 2: the context-conditioned surface: a Flow with an embedding net whose RQ couplings use
+    context-conditioned ResidualNets (GLU gates, resnet.py:50-51), log_prob / sample_and_log_prob with a context batch."""
+    rec = {}
+    with torch.no_grad():
+        torch.manual_seed(20)
+        features, ctx_raw, ctx = 16, 5, 6
+        steps = []
+        for i in range(3):
+            steps.append(T.ActNorm(features))
+            steps.append(T.CompositeTransform([T.RandomPermutation(features), T.LULinear(features, identity_init=True)]))
+            steps.append(T.PiecewiseRationalQuadraticCouplingTransform(
+                mask=torchutils.create_alternating_binary_mask(features, even=(i % 2 == 0)),
+                transform_net_create_fn=lambda i_, o_: ResidualNet(i_, o_, hidden_features=32, context_features=ctx, num_blocks=2),
+                num_bins=8, tails="linear", tail_bound=3.0))
+        flow = Flow(T.CompositeTransform(steps), StandardNormal([features]), embedding_net=torch.nn.Linear(ctx_raw, ctx)).eval()
+        perturb(flow)
+        x = torch.randn(300, features)
+        c = torch.randn(300, ctx_raw)
+        lp = flow.log_prob(x, context=c)
+        z = flow.transform_to_noise(x, context=c)
+        lp64 = flow.double().log_prob(x.double(), context=c.double())
+        flow.float()
+        noise = torch.randn(300, features)
+        xs, _ = flow._transform.inverse(noise, context=flow._embedding_net(c))
+        rec["context_flow"] = dict(sd=flow.state_dict(), x=x, context=c, log_prob=lp, z=z, log_prob_fp64=lp64, noise=noise, sample=xs)
+    save("context_rows", rec)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "next_rows":
         next_rows()
+    elif len(sys.argv) > 1 and sys.argv[1] == "context_rows":
+        context_rows()
     else:
         main()
         next_rows()
+        context_rows()

@@ -528,6 +528,36 @@ def test_next_rows_against_reference_goldens(cuda_device):
 
 
 @torch.no_grad()
+def test_context_conditioned_flow_against_reference_golden(cuda_device):
+    """Flow with an embedding net and context-conditioned ResidualNet conditioners (GLU gates) -- reference
+    outputs in tests/golden/context_rows.pt.  The folded affine runs and the spline epilogue run on our kernels; the gated
+    conditioner itself is evaluated by torch on the GPU (dense_chain() declines a context)."""
+    from nflows_b200.distributions.normal import StandardNormal
+    from nflows_b200.flows import Flow
+    g = load_golden("context_rows")["context_flow"]
+    features, ctx_raw, ctx = 16, 5, 6
+    steps = []
+    for i in range(3):
+        steps.append(T.ActNorm(features))
+        steps.append(T.CompositeTransform([T.RandomPermutation(features), T.LULinear(features, identity_init=True)]))
+        steps.append(T.PiecewiseRationalQuadraticCouplingTransform(
+            mask=torchutils.create_alternating_binary_mask(features, even=(i % 2 == 0)),
+            transform_net_create_fn=lambda i_, o_: ResidualNet(i_, o_, hidden_features=32, context_features=ctx, num_blocks=2),
+            num_bins=8, tails="linear", tail_bound=3.0))
+    flow = Flow(T.CompositeTransform(steps), StandardNormal([features]), embedding_net=torch.nn.Linear(ctx_raw, ctx)).eval()
+    flow.load_state_dict(g["sd"], strict=True)
+    flow = flow.to(cuda_device)
+    x, c = g["x"].to(cuda_device), g["context"].to(cuda_device)
+    with native_launches():
+        lp = flow.log_prob(x, context=c)
+    assert rel_err(lp.cpu(), g["log_prob_fp64"]) <= max(TOL, 3 * rel_err(g["log_prob"], g["log_prob_fp64"]))
+    assert rel_err(flow.transform_to_noise(x, context=c).cpu(), g["z"]) <= 5e-5
+    xs, _ = flow._transform.inverse(g["noise"].to(cuda_device), context=flow._embedding_net(c))
+    assert rel_err(xs.cpu(), g["sample"]) <= 1e-3          # 3 spline inverses in a row: the reference's own round trip is ~1e-3
+    assert flow.sample(4, context=c[:5]).shape == (5, 4, features)
+
+
+@torch.no_grad()
 def test_autoregressive_rq_transform_cfg4(cuda_device):
     """BASELINE configs[3]: MaskedPiecewiseRationalQuadraticAutoregressiveTransform D=64 K=8 -- forward (one MADE pass on the
     tensor-core dense chain + fused spline kernel) and the 64-pass inverse, against the reference's outputs."""
