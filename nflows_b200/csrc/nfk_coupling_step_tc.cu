@@ -35,6 +35,13 @@ namespace nfk {
 namespace tc {
 
 constexpr int STEP_MAX_LAYERS = 9;                                   // initial layer + up to 8 square layers
+// K-slabs accumulated inside the tensor core (round-toward-zero adds) before a partial sum is drained to registers.  Draining is
+// not free: TMEM reads run at ~64 B/clk per SM, a 128 x 192 fp32 partial sum is 1536 cycles of that against 96 cycles per MMA.
+// Final layer (spline logits, insensitive): the whole K = 256 in one partial sum; trunk layers: K = 128 per partial sum.
+// Measured (cfg 3, 2^20 rows, parity_check of bench.py against the CPU oracle): final 4 -> 8: 182 -> 175 ms in this kernel,
+// rel. error 2.2e-6 -> 2.4e-6; trunk 2 -> 4: -2 ms, unchanged error (profiles/drain_sweep_r2.txt).
+constexpr int STEP_DRAIN_FINAL_DEFAULT = 8;
+constexpr int STEP_DRAIN_TRUNK_DEFAULT = 4;
 constexpr int STEP_SLAB_BYTES = 2 * A_BYTES;                         // one K-slab of R: hi | lo
 constexpr int STEP_R_BYTES = (BN_MAX / BK) * STEP_SLAB_BYTES;        // 128 KB
 constexpr int STEP_RING_BYTES = 80 * 1024;
@@ -189,8 +196,8 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
         if (warp == 0) {
-            // ================================================= TMA producer (one thread)
-            if (lane == 0) {
+            // ================================================= TMA producer (one elected thread: uniform datapath, see elect_one)
+            if (elect_one()) {
                 uint32_t uses = 0;                                   // bit s: parity of the number of loads issued into ring slot s
                 auto slot_wait = [&](int s) { mbar_wait(bar_empty + 8 * s, ((uses >> s) & 1u) ^ 1u); };   // last use released by every CTA
                 auto drain = [&]() {
@@ -313,13 +320,14 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                 }
             }
         } else if (warp == 1 || (warp == 3 && p.mma_warps == 2)) {
-            // ================================================= MMA issuers (whole warp runs the loop, lane 0 issues).
+            // ================================================= MMA issuers (one elected thread per issuing warp).
             // TWO issuing warps take alternate partial sums (warp 1: TMEM buffer 0, warp 3: buffer 1): what limited the tensor
             // pipe was the issue sequence itself -- every tcgen05.mma is preceded by an ELECT and five R2UR moves of its
             // descriptors into uniform registers, ~190 cycles per instruction against 96 cycles of tensor work at N = 192 (ncu r2:
             // the issuing warp never waited on a barrier, tensor pipe 50 %).  The MMAs of one partial sum come from one warp, in
             // program order, so results do not depend on how the two warps interleave.
-            const bool leader = lane == 0;
+            if (elect_one()) {                                       // ONE elected thread runs the role (uniform datapath)
+            const bool leader = true;
             const int my = warp == 1 ? 0 : 1;
             const bool solo = p.mma_warps != 2;
             uint32_t seen = 0;                                       // bit s: parity of the number of fills of ring slot s consumed
@@ -449,6 +457,7 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         }
                     }
                 }
+            }
             }
         }
     } else {
@@ -864,15 +873,15 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
     NFK_REQUIRE(d->n_rows < (1ll << 31), "n_rows too large for one launch");
     tc::StepParams p;
     memset(&p, 0, sizeof(p));
-    p.drain_f = tc::DRAIN_SLABS_FUSED;
+    p.drain_f = tc::STEP_DRAIN_FINAL_DEFAULT;
     {
         static int mma_pref = 0, drain_t_pref = 0;
         if (!mma_pref) {
             const char* e = getenv("NFK_STEP_MMA_WARPS");
             mma_pref = (e && e[0] == '2') ? 2 : 1;
             const char* t = getenv("NFK_STEP_TRUNK_DRAIN");
-            drain_t_pref = t ? atoi(t) : tc::DRAIN_SLABS_LINEAR;
-            if (drain_t_pref < 1) drain_t_pref = tc::DRAIN_SLABS_LINEAR;
+            drain_t_pref = t ? atoi(t) : tc::STEP_DRAIN_TRUNK_DEFAULT;
+            if (drain_t_pref < 1) drain_t_pref = tc::STEP_DRAIN_TRUNK_DEFAULT;
         }
         p.mma_warps = mma_pref;
         p.drain_t = drain_t_pref;
@@ -911,8 +920,8 @@ extern "C" int nfk_rq_coupling_step_f16x3(const NfkCouplingStep* d, void* stream
         static int drain_pref = 0;
         if (!drain_pref) {
             const char* e = getenv("NFK_STEP_DRAIN");
-            drain_pref = e ? atoi(e) : tc::DRAIN_SLABS_FUSED;
-            if (drain_pref < 1) drain_pref = tc::DRAIN_SLABS_FUSED;
+            drain_pref = e ? atoi(e) : tc::STEP_DRAIN_FINAL_DEFAULT;
+            if (drain_pref < 1) drain_pref = tc::STEP_DRAIN_FINAL_DEFAULT;
         }
         p.drain_f = drain_pref;
     }

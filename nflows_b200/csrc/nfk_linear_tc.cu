@@ -164,8 +164,9 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");     // hand registers to the epilogue warpgroups
     if (warp == 0) {
-        // ================================================= TMA producer of the A ring (this CTA's 128 rows of every K-slab)
-        if (lane == 0) {
+        // ================================================= TMA producer of the A ring (this CTA's 128 rows of every K-slab); one
+        // ELECTED thread, so that ptxas keeps the role on the uniform datapath (tc_common.cuh: elect_one)
+        if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             int tm, tn;
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
@@ -191,7 +192,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     } else if (warp == 2) {
         // ================================================= TMA producer of the W ring (each CTA of a cluster fetches half of every
         // weight slab and multicasts it to both)
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t tx_bytes = 2u * (uint32_t)p.BN * ROW_BYTES;
             int stage = 0; uint32_t phase = 0;
             int tm, tn;
@@ -224,14 +225,14 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             }
         }
     } else if ((warp == 1 || (warp == 3 && p.mma_warps == 2)) && (!PAIR || cta_rank == 0)) {
-        // ================================================= MMA issuers.  The whole warp runs the loop (so stage indices and
-        // shared-memory descriptors stay in uniform registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
+        // ================================================= MMA issuers: one ELECTED thread per issuing warp (uniform datapath:
+        // descriptors in uniform registers, tcgen05.mma back to back -- see tc_common.cuh: elect_one).
         // Per K-slab: the two small cross terms (a_lo w_hi, a_hi w_lo), then the main product, then both ring slots are released;
         // a partial sum (one TMEM buffer) covers DRAIN_SLABS_LINEAR slabs.  TWO issuing warps take alternate partial sums (warp 1:
         // buffer 0, warp 3: buffer 1): every tcgen05.mma costs the issuing thread ~190 cycles of ELECT / R2UR operand moves
         // against ~100 cycles of tensor work, so one issuer left the tensor pipe half idle (ncu r2).
-        {
-            const bool leader = lane == 0;
+        if (elect_one()) {
+            const bool leader = true;
             const int my = warp == 1 ? 0 : 1;
             const bool solo = p.mma_warps != 2;
             const uint32_t idesc = make_idesc(p.BN, PAIR ? 2 * BM : BM);

@@ -141,8 +141,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
         if (warp == 0) {
-            // ================================================= TMA producer
-            if (lane == 0) {
+            // ================================================= TMA producer (one elected thread: uniform datapath, tc_common.cuh)
+            if (elect_one()) {
                 // bytes counted on the slab's barrier: MODE 1/2 everything landing in THIS CTA's slab; MODE 3 both CTAs' loads
                 // (A of both + both halves of W) on the leader's barrier
                 constexpr uint32_t tx_bytes = PAIR ? 2u * (2u * A_BYTES + (uint32_t)BN * ROW_BYTES)
@@ -195,8 +195,8 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
         } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
             // ================================================= MMA issuer: one partial sum per DRAIN_SLABS_FUSED slabs.  The whole warp
             // runs the loop (stage indices / descriptors stay uniform); only lane 0 issues tcgen05.mma / tcgen05.commit.
-            {
-                const bool leader = lane == 0;
+            if (elect_one()) {                       // one elected thread runs the role (uniform datapath, tc_common.cuh: elect_one)
+                const bool leader = true;
                 const uint32_t idesc = make_idesc(BN, PAIR ? 2 * BM : BM);
                 int stage = 0; uint32_t phase = 0;
                 int acc = 0; uint32_t acc_phase = 0;

@@ -101,8 +101,8 @@ residual_trunk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
         if (warp == 0) {
-            // ================================================= TMA producer (one thread): input pair, weight stream, output stores
-            if (lane == 0) {
+            // ================================================= TMA producer (one elected thread): input pair, weight stream, output stores
+            if (elect_one()) {
                 const uint32_t w_tx = 2u * (uint32_t)p.H * ROW_BYTES;
                 const int wrows = p.H / CL;
                 int stage = 0; uint32_t phase = 0, out_phase = 0;
@@ -143,8 +143,9 @@ residual_trunk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                 }
             }
         } else if (warp == 1) {
-            // ================================================= MMA issuer (whole warp runs the loop, lane 0 issues)
-            const bool leader = lane == 0;
+            // ================================================= MMA issuer (one elected thread: uniform datapath, tc_common.cuh)
+            if (elect_one()) {
+            const bool leader = true;
             const uint32_t idesc = make_idesc(p.H);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -195,6 +196,7 @@ residual_trunk_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     }
                 }
+            }
             }
         }
     } else {

@@ -73,6 +73,22 @@ __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtens
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
+// One lane of a converged warp (elect.sync).  Code that issues tcgen05.mma / TMA under `if (elect_one())` is compiled onto the
+// UNIFORM datapath: descriptors live in uniform registers and UTCHMMA / UTMALDG issue back to back.  Under `if (lane == 0)` ptxas
+// cannot know a single lane is active and wraps EVERY such instruction in an ELECT + five R2UR moves + a lane loop (~190 cycles
+// per tcgen05.mma measured, against 96-128 cycles of tensor work: the issuing warp, never idle, was what capped the tensor pipe
+// at ~50 % in every tensor-core kernel of this library up to round 2).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -1,0 +1,41 @@
+#!/bin/bash
+# Round 2, GPU call 8: elected single-thread MMA / TMA roles (uniform datapath) in every tensor-core kernel; drain defaults 8 / 4 / 2.
+mkdir -p gpurun_out
+LOG=gpurun_out/call8.log
+: > $LOG
+run() { echo "--- $*" >> $LOG; timeout 240 "$@" >> $LOG 2>&1; echo "rc=$?" >> $LOG; }
+for s in t1 t3 t4 c0 c1 c2 c3 c4 c6 c8; do run python scripts/step_check.py $s; done
+NFK_CLUSTER=1 run python scripts/step_check.py c1
+echo "=== pytest gpu" >> $LOG
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -12 >> $LOG
+echo "=== r1 launch sequence (fallback kernels) still green?" >> $LOG
+NFLOWS_B200_STEP_KERNEL=0 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 >> $LOG
+NFLOWS_B200_STEP_KERNEL=0 NFLOWS_B200_TRUNK_KERNEL=1 timeout 300 python -m pytest tests/test_trunk_kernel.py -m gpu -q 2>&1 | tail -2 >> $LOG
+for d in 2 4 8; do
+  echo "=== NFK_LINEAR_DRAIN=$d" >> $LOG
+  NFK_LINEAR_DRAIN=$d run python scripts/linear_only.py 784 784 pair
+done
+run python scripts/linear_only.py 256 256 pair
+run python scripts/spline_only.py
+bench() {
+  tag=$1; shift
+  env "$@" timeout 500 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-spline-roofline $EXTRA 2>gpurun_out/bench8_$tag.err | tail -1 > gpurun_out/bench8_$tag.json
+  python - "$tag" >> $LOG <<'PY'
+import json, sys
+try:
+    d = json.load(open("gpurun_out/bench8_%s.json" % sys.argv[1]))
+    print(sys.argv[1], "samples/s %.0f" % d["value"], "ms/step %.1f" % d["ms_per_step"], "clk", d["clocks"]["sm_mhz"], d["timeline_ms_per_step"], "parity", d["parity_check"]["rel_err"], d["parity_check"]["ok"], "e2e", d["e2e"]["value"], "extra", d.get("extra"))
+except Exception as e:
+    print("bench failed", sys.argv[1], e)
+PY
+  tail -2 gpurun_out/bench8_$tag.err >> $LOG
+}
+EXTRA="" bench default A=1
+EXTRA="--no-extras" bench fdrain4 NFK_STEP_DRAIN=4
+EXTRA="--no-extras" bench ldrain4 NFK_LINEAR_DRAIN=4
+EXTRA="--no-extras" bench ewg2 NFK_STEP_EWG=2
+EXTRA="--no-extras" bench r1path NFLOWS_B200_STEP_KERNEL=0
+echo "=== ncu" >> $LOG
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rq_coupling_step -s 4 -c 1 -o gpurun_out/ncu_step_r2f -f python bench.py --steps 1 --warmup 1 --rows 262144 --no-cpu-baseline --no-spline-roofline --no-extras --no-parity-check 2>&1 | tail -2 >> $LOG
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_f16x3 -s 4 -c 1 -o gpurun_out/ncu_linear_r2f -f python bench.py --steps 1 --warmup 1 --rows 262144 --no-cpu-baseline --no-spline-roofline --no-extras --no-parity-check 2>&1 | tail -2 >> $LOG
+cat $LOG
