@@ -111,6 +111,7 @@ struct StepParams {
     int mma_warps;                // 2: two MMA-issuing warps take alternate partial sums; 1: one issuer
     int drain_t;                  // K-slabs accumulated in TMEM per partial sum of a trunk layer (DRAIN_SLABS_LINEAR by default)
     int drain_f;                  // K-slabs accumulated in TMEM per partial sum of the final layer (DRAIN_SLABS_FUSED, or all)
+    uint32_t zero;                // always 0 (mbar_arrive_after_loads)
     int tma_x;                    // inputs of the transformed features arrive as TMA boxes (consecutive columns, 16-byte aligned)
     float out_scale;
     float* lad_accum;
@@ -631,8 +632,12 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     const float* xt = reinterpret_cast<const float*>(smem_gen + X_TILE_OFF + xslot * (BM * TF * 4)) + r_tile * TF + wg * FPT;
 #pragma unroll
                     for (int f = 0; f < FPT; ++f) xin[f] = (row_ok && j0 + f < p.d_t) ? xt[f] : 0.0f;
+                    // the slot goes back to the producer only once the loads have RETURNED (mbar_arrive_after_loads)
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int f = 0; f < FPT; ++f) bits |= __float_as_uint(xin[f]);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_xempty + 8 * xslot);
+                    if (lane == 0) mbar_arrive_after_loads(bar_xempty + 8 * xslot, bits, p.zero);
                     if (++xslot == 2) { xslot = 0; xphase ^= 1; }
                 } else {
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -650,8 +655,11 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         sum[c] = fmaf(sum[c], p.inv_acc_scale_f, b4.x); sum[c + 1] = fmaf(sum[c + 1], p.inv_acc_scale_f, b4.y);
                         sum[c + 2] = fmaf(sum[c + 2], p.inv_acc_scale_f, b4.z); sum[c + 3] = fmaf(sum[c + 3], p.inv_acc_scale_f, b4.w);
                     }
+                    uint32_t bits = 0;                    // one component of every LDS.128 (mbar_arrive_after_loads)
+#pragma unroll
+                    for (int c = 0; c < HC; c += 4) bits |= __float_as_uint(sum[c]);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_bempty + 8 * bslot);
+                    if (lane == 0) mbar_arrive_after_loads(bar_bempty + 8 * bslot, bits, p.zero);
                     if (++bslot == 2) { bslot = 0; bphase ^= 1; }
                 }
                 // ---- spline on the FPT features held in registers

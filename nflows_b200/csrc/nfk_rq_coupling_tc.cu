@@ -36,6 +36,7 @@ struct FusedParams {
     int inverse;
     float acc_scale;        // 2^(e_a + e_w): the accumulators hold (A Wp^T) * acc_scale (fp16 pairs are power-of-two scaled)
     float inv_acc_scale;
+    uint32_t zero;          // always 0 (mbar_arrive_after_loads)
     SplineParams sp;
 };
 
@@ -335,8 +336,11 @@ rq_coupling_final_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
                         sum[c] = fmaf(sum[c], p.inv_acc_scale, b4.x); sum[c + 1] = fmaf(sum[c + 1], p.inv_acc_scale, b4.y);
                         sum[c + 2] = fmaf(sum[c + 2], p.inv_acc_scale, b4.z); sum[c + 3] = fmaf(sum[c + 3], p.inv_acc_scale, b4.w);
                     }
+                    uint32_t bits = 0;                    // one component of every LDS.128 (mbar_arrive_after_loads)
+#pragma unroll
+                    for (int c = 0; c < HC; c += 4) bits |= __float_as_uint(sum[c]);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_bempty + 8 * bslot);
+                    if (lane == 0) mbar_arrive_after_loads(bar_bempty + 8 * bslot, bits, p.zero);
                     if (++bslot == 2) { bslot = 0; bphase ^= 1; }
                 }
                 // ---- spline on the FPT features held in registers, all features advanced together (ILP = FPT)
@@ -534,6 +538,7 @@ extern "C" int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int invers
     const __half* a_hi = (const __half*)a_hi_; const __half* a_lo = (const __half*)a_lo_;
     const __half* wp_hi = (const __half*)wp_hi_; const __half* wp_lo = (const __half*)wp_lo_;
     tc::FusedParams p;
+    p.zero = 0;
     int rc = make_spline_params(desc, &p.sp);
     if (rc) return rc;
     NFK_REQUIRE(n_rows >= 0 && d_t >= 1 && hidden_features >= 1, "bad sizes");

@@ -78,6 +78,17 @@ __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtens
 // cannot know a single lane is active and wraps EVERY such instruction in an ELECT + five R2UR moves + a lane loop (~190 cycles
 // per tcgen05.mma measured, against 96-128 cycles of tensor work: the issuing warp, never idle, was what capped the tensor pipe
 // at ~50 % in every tensor-core kernel of this library up to round 2).
+// Hands a TMA-filled shared-memory slot back to its producer AFTER this warp's loads from it have returned.  mbarrier.arrive
+// is not ordered behind earlier LDS of the same warp (ptxas schedules it two instructions after the last LDS.128 and the barrier
+// unit does not wait for the load queue), so the producer's next bulk copy could overwrite the slot under a load still queued:
+// measured on hardware (r2) as the last float4 of a warp's bias window holding the bias of column tile n+2.  Two guards:
+// the generic->async proxy fence, and a true data dependency -- the barrier address is offset by (loaded bits & zero), `zero`
+// a kernel parameter that is always 0, which ptxas cannot fold away.
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t loaded_bits, uint32_t zero) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive(bar + (loaded_bits & zero));
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(

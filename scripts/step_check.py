@@ -83,6 +83,14 @@ def coupling(features, hidden, blocks, rows, bins=8, tails="linear", inverse=Fal
         rows_bad = torch.nonzero(bad.max(dim=1).values > 1e-3).flatten()
         cols_bad = torch.nonzero(bad.max(dim=0).values > 1e-3).flatten()
         print("   bad rows %d (first %s) bad cols %d (first %s)" % (rows_bad.numel(), rows_bad[:12].tolist(), cols_bad.numel(), cols_bad[:24].tolist()))
+        idx = torch.nonzero(bad > 1e-3)
+        tf = t.transform_features.cpu().tolist()
+        for r_, c_ in idx[:24].tolist():
+            j = tf.index(c_) if c_ in tf else -1
+            print("      row %d (tile %d, r %d) col %d (feature %d: tile n=%d, slot %d) got %.5f want %.5f x %.5f r1path %.5f" % (
+                r_, r_ // 128, r_ % 128, c_, j, j // 8, j % 8, float(y[r_, c_]), float(want_y[r_, c_]), float(x[r_, c_]), float(y0[r_, c_])))
+        tiles = sorted(set((r_ // 128) for r_, _ in idx.tolist()))
+        print("      tiles with errors:", tiles[:40], "features:", sorted(set(tf.index(c_) for _, c_ in idx.tolist() if c_ in tf))[:40])
 
 
 STAGES = {
