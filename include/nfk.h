@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NFK_ABI_VERSION 3
+#define NFK_ABI_VERSION 4
 
 #define NFK_OK 0
 #define NFK_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -111,6 +111,13 @@ int nfk_linear_f16x3(const void* a_hi, const void* a_lo, int64_t lda, int32_t a_
 int nfk_absmax(const float* x, int64_t ldx, int64_t n_rows, int32_t n_cols, float* out, void* stream);
 int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int relu, int32_t scale_exp, void* hi, void* lo, int64_t ldo,
                   int64_t n_rows, int32_t* flags, void* stream);
+
+/* Context gate + skip connection of a residual block (nn/nets/resnet.py:50-53: `F.glu(cat(temps, context_layer(context)))`
+ * then `inputs + temps`):  v = skip + t * sigmoid(gate)  (skip may be NULL).  Writes v as fp32 (y, may be NULL) and / or as the
+ * fp16 pair of pre(v) * 2^y_exp (pre = relu when split_relu) that the next dense layer multiplies. */
+int nfk_glu_skip_rows(const float* t, int64_t ldt, const float* gate, int64_t ldg, const float* skip, int64_t ldsk, float* y,
+                      int64_t ldy, void* y_hi, void* y_lo, int64_t lds, int32_t y_exp, int split_relu, int64_t n_rows,
+                      int32_t n_cols, int32_t* flags, void* stream);
 
 /* EXPERIMENTAL (not yet validated on hardware; the host code uses it only when NFLOWS_B200_TRUNK_KERNEL=1).
  * The square layers of a conditioner trunk (the residual blocks of ResidualNet, nn/nets/resnet.py:9-55) as ONE persistent
@@ -221,6 +228,26 @@ int nfk_affine_coupling_rows(const float* x, int64_t ldx, const float* params, i
  * out[n] = (-0.5 * sum_j z[n, j]^2 - log_z) + (lad ? lad[n] : 0). */
 int nfk_std_normal_log_prob(const float* z, int64_t ldz, int32_t d, float log_z, const float* lad, float* out,
                             int64_t n_rows, void* stream);
+
+/* ---- image path: per-pixel form of the 4-D transforms ------------------------ */
+/* Inside a native image chain the tensor is PIXEL ROWS [n_images*H*W, C] fp32 (channels last); the 4-D ActNorm,
+ * OneByOneConvolution and channel-wise coupling (normalization.py:178-186, conv.py:17-29, coupling.py:280-285) are then
+ * the 2-D entry points above applied to those rows.
+ * nfk_nchw_to_rows: x [n_images, channels, pixels] <-> rows [n_images*pixels, channels] (to_nchw = 0: x -> rows, reads
+ * `x`, writes `rows`; to_nchw = 1: reads `x` as rows, writes `rows` as NCHW -- the first pointer is always the source). */
+int nfk_nchw_to_rows(const float* src, float* dst, int64_t n_images, int32_t channels, int32_t pixels, int to_nchw, void* stream);
+/* SqueezeTransform (reshape.py:7-68, factor 2) on pixel rows.  h2 x w2 is the SQUEEZED grid, channels the UNSQUEEZED channel
+ * count: forward reads [n*2h2*2w2, channels] and writes [n*h2*w2, 4*channels] with channel c*4 + dy*2 + dx = pixel (dy, dx)
+ * of the 2x2 window of channel c; inverse the other way round. */
+int nfk_squeeze_rows(const float* in, float* out, int64_t n_images, int32_t h2, int32_t w2, int32_t channels, int inverse,
+                     void* stream);
+/* K-major operand of a 3x3, padding-1 convolution (nn.Conv2d in ConvResidualBlock, nn/nets/resnet.py:103-160) from the fp16
+ * pair of its (already activated) input: out[(b,y,x), (ky*3+kx)*channels + c] = in[(b, y+ky-1, x+kx-1), c], 0 outside the image.
+ * The convolution is then nfk_linear_f16x3 with the weight reshaped to [out_channels, 9*channels] in (ky, kx, c) order. */
+int nfk_im2col3x3_f16(const void* hi, const void* lo, int64_t lds, void* out_hi, void* out_lo, int64_t ldo, int64_t n_images,
+                      int32_t h, int32_t w, int32_t channels, void* stream);
+/* out_accum[s] += sum of values[s*segment_len .. +segment_len): per-pixel log|det| -> per-sample (sum_except_batch over H, W). */
+int nfk_segment_sum(const float* values, float* out_accum, int64_t n_segments, int32_t segment_len, void* stream);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,12 @@ _SIGNATURES = {
                                  c_int32, c_int32, c_int32, c_int, c_int, c_int64, c_int32, c_int32, _P, _P]),
     "nfk_absmax": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P]),
     "nfk_split_f16": (c_int, [_P, c_int64, c_int32, c_int, c_int32, _P, _P, c_int64, c_int64, _P, _P]),
+    "nfk_nchw_to_rows": (c_int, [_P, _P, c_int64, c_int32, c_int32, c_int, _P]),
+    "nfk_squeeze_rows": (c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, c_int, _P]),
+    "nfk_im2col3x3_f16": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
+    "nfk_segment_sum": (c_int, [_P, _P, c_int64, c_int32, _P]),
+    "nfk_glu_skip_rows": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int, c_int64, c_int32,
+                                  _P, _P]),
     "nfk_residual_trunk_f16x3_supported": (c_int, [c_int32, c_int32, c_int64, c_int64]),
     "nfk_residual_trunk_f16x3": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P, c_int64, _P, _P,
                                          c_int64, c_int64, c_int32, _P, _P]),
@@ -105,8 +111,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError here means header and library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.nfk_version() != 3:
-        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 3".format(lib.nfk_version()))
+    if lib.nfk_version() != 4:
+        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 4".format(lib.nfk_version()))
     _lib = lib
     return lib
 

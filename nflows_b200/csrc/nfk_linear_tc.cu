@@ -621,6 +621,31 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
     if (flag && flags) atomicOr(flags, flag);
 }
 
+// Context gate of a residual block (nn/nets/resnet.py:50-53): y = skip + t * sigmoid(gate), i.e. F.glu(cat(t, gate)) + inputs,
+// in one pass; writes the fp32 result (the next block's skip tensor) and/or the fp16 pair the next dense layer multiplies.
+__global__ void __launch_bounds__(256) glu_skip_kernel(const float* __restrict__ t, int64_t ldt, const float* __restrict__ gate,
+                                                       int64_t ldg, const float* __restrict__ skip, int64_t ldsk, float* __restrict__ y,
+                                                       int64_t ldy, __half* __restrict__ hi, __half* __restrict__ lo, int64_t ldo,
+                                                       float scale, int relu, int64_t n_rows, int n_cols, int32_t* flags) {
+    int flag = 0;
+    const int64_t total = n_rows * n_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n_cols;
+        const int j = (int)(i - r * n_cols);
+        const float g = gate[r * ldg + j];
+        float v = t[r * ldt + j] * (1.0f / (1.0f + expf(-g)));
+        if (skip) v += skip[r * ldsk + j];
+        if (y) y[r * ldy + j] = v;
+        if (hi) {
+            __half h, l;
+            split_f16(relu ? fmaxf(v, 0.0f) : v, scale, h, l, flag);
+            hi[r * ldo + j] = h;
+            lo[r * ldo + j] = l;
+        }
+    }
+    if (flag && flags) atomicOr(flags, flag);
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -735,6 +760,21 @@ extern "C" int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int re
     tc::split_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, n_cols, relu, ldexpf(1.0f, scale_exp), (__half*)hi, (__half*)lo,
                                                                  ldo, n_rows, vec4, flags);
     return check_launch("split_f16_kernel");
+}
+
+extern "C" int nfk_glu_skip_rows(const float* t, int64_t ldt, const float* gate, int64_t ldg, const float* skip, int64_t ldsk,
+                                 float* y, int64_t ldy, void* y_hi, void* y_lo, int64_t lds, int32_t y_exp, int split_relu,
+                                 int64_t n_rows, int32_t n_cols, int32_t* flags, void* stream) {
+    NFK_REQUIRE(n_rows >= 0 && n_cols >= 0 && pow2_exp_ok(y_exp), "bad sizes");
+    if (n_rows == 0 || n_cols == 0) return NFK_OK;
+    NFK_REQUIRE(t && gate, "NULL pointer");
+    NFK_REQUIRE(y || (y_hi && y_lo), "no output requested");
+    NFK_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "y_hi and y_lo must be given together");
+    int64_t blocks = (n_rows * n_cols + 255) / 256;
+    int grid = (int)(blocks > 148 * 32 ? 148 * 32 : blocks);
+    tc::glu_skip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, ldt, gate, ldg, skip, ldsk, y, ldy, (__half*)y_hi, (__half*)y_lo, lds,
+                                                                ldexpf(1.0f, y_exp), split_relu, n_rows, n_cols, flags);
+    return check_launch("glu_skip_kernel");
 }
 
 // fp16 rows must start on 16-byte boundaries for TMA: leading dimensions and K multiples of 8

@@ -49,8 +49,14 @@ def chain_uses_tc(chain, first_in_features):
     if backend() != "tc":
         return False
     k = first_in_features
-    for weight, _, _, _, _ in chain:
-        if weight.shape[1] != k or not K.f16x3_supported(k, weight.stride(0), k):
+    conv = getattr(chain, "conv3x3", ())
+    if isinstance(chain, ConvChain):
+        if k != chain.in_features or current_geometry() is None:
+            return False
+        k = chain.in_pad
+    for i, (weight, _, _, _, _) in enumerate(chain):
+        kk = 9 * k if i in conv else k
+        if weight.shape[1] != kk or not K.f16x3_supported(kk, weight.stride(0), kk):
             return False
         k = weight.shape[0]
     return True
@@ -206,6 +212,80 @@ def step_plan(chain):
     return hit[1]
 
 
+class Chain(list):
+    """A dense chain whose layers also see a context tensor (ResidualNet with context_features, nn/nets/resnet.py:36-100):
+    layer 0 carries residual token "ctx_init" (add W0[:, d_id:] context + b0: the reference concatenates [inputs, context] in
+    front of the initial layer), the second layer of every block "glu_skip" (inputs + t * sigmoid(context_layer(context))).
+    ctx_init = (weight padded to a multiple of 8 columns, bias, unpadded weight); ctx_gates[i] likewise for layer i."""
+
+    def __init__(self, layers, context, ctx_init, ctx_gates, ctx_pad):
+        super().__init__(layers)
+        self.context, self.ctx_init, self.ctx_gates, self.ctx_pad = context, ctx_init, ctx_gates, ctx_pad
+        self._pair = None
+
+    def context_pair(self, flags=None):
+        """Pair16 of the context, zero padded to ctx_pad columns (TMA rows are multiples of 16 bytes); split once per call."""
+        if self._pair is None:
+            n, c = self.context.shape
+            self._pair = K.Pair16.zeros(n, self.ctx_pad, act_exp(), self.context.device) if c != self.ctx_pad else \
+                K.Pair16.empty(n, c, act_exp(), self.context.device)
+            K.split_f16(self.context, act_exp(), out=self._pair.cols(0, c), flags=flags)
+        return self._pair
+
+    def rows(self, r0, r1):
+        part = Chain(list(self), self.context[r0:r1], self.ctx_init, self.ctx_gates, self.ctx_pad)
+        if self._pair is not None:
+            part._pair = self._pair.rows(r0, r1)
+        return part
+
+
+_IMAGE_GEOMETRY = [None]
+
+
+class image_geometry:
+    """`with image_geometry(b, h, w)`: the 2-D rows flowing through the native chain are the pixels of b images of h x w (channels
+    last).  3x3 convolutions of a ConvChain need it; row blocks are kept to whole images while it is set."""
+
+    def __init__(self, b, h, w):
+        self.geom = (int(b), int(h), int(w))
+
+    def __enter__(self):
+        self.prev, _IMAGE_GEOMETRY[0] = _IMAGE_GEOMETRY[0], self.geom
+        return self
+
+    def __exit__(self, *exc):
+        _IMAGE_GEOMETRY[0] = self.prev
+
+
+def current_geometry():
+    return _IMAGE_GEOMETRY[0]
+
+
+def whole_images(rows):
+    """`rows` rounded down to a multiple of the pixels per image (row blocks of an image chain), at least one image."""
+    g = _IMAGE_GEOMETRY[0]
+    if g is None:
+        return rows
+    hw = g[1] * g[2]
+    return max(hw, rows // hw * hw)
+
+
+class ConvChain(list):
+    """Dense chain of a ConvResidualNet (nn/nets/resnet.py:103-205 of the reference) on pixel rows: 1x1 convolutions are dense
+    layers as they stand; the layers listed in `conv3x3` are 3x3 / padding-1 convolutions whose weight is stored reshaped to
+    [out, 9*in] in (ky, kx, c) order and whose operand is the im2col of the incoming pair (kernels.im2col3x3).  `in_pad`: the
+    initial layer's weight is zero padded to this many columns (a TMA row is a multiple of 16 bytes; cfg 5 has 6 and 12 identity
+    channels)."""
+
+    def __init__(self, layers, conv3x3, in_features, in_pad):
+        super().__init__(layers)
+        self.conv3x3, self.in_features, self.in_pad = frozenset(conv3x3), in_features, in_pad
+
+
+def chain_rows(chain, r0, r1):
+    return chain.rows(r0, r1) if isinstance(chain, Chain) else chain
+
+
 class ChainState:
     """Activation between two layers: fp32 tensor (`raw`, FFMA path) or the Pair16 a tensor-core layer consumes."""
 
@@ -220,14 +300,14 @@ def run_trunk(chain, x, id_cols, use_tc, x_pair=None, flags=None):
     The tensor-core path walks row sub-blocks (config.trunk_block_rows)."""
     from . import config
     n = x.shape[0]
-    step = max(128, int(config.trunk_block_rows))
+    step = whole_images(max(128, int(config.trunk_block_rows)))
     if use_tc and n > step and len(chain) > 1:
         width = chain[-2][0].shape[0]
         dst = K.Pair16.empty(n, width, act_exp(), x.device)
         for r0 in range(0, n, step):
             r1 = min(n, r0 + step)
-            _run_trunk_block(chain, x[r0:r1], id_cols, True, dst.rows(r0, r1), None if x_pair is None else x_pair.rows(r0, r1),
-                             flags)
+            _run_trunk_block(chain_rows(chain, r0, r1), x[r0:r1], id_cols, True, dst.rows(r0, r1),
+                             None if x_pair is None else x_pair.rows(r0, r1), flags)
         return ChainState(pair=dst)
     return _run_trunk_block(chain, x, id_cols, use_tc, None, x_pair, flags)
 
@@ -238,9 +318,16 @@ def _run_trunk_block(chain, x, id_cols, use_tc, last_out, x_pair, flags):
     if use_tc:
         # every layer's epilogue writes the Pair16 the next layer consumes (pre-activated for it) and, where a residual
         # block needs its input again, the fp32 tensor as well
+        in_pad = getattr(chain, "in_pad", None)
         if x_pair is None:
             x_id = x if id_cols is None else K.gather_cols(x, id_cols)
-            x_pair = K.split_f16(x_id, act_exp(), relu=body[0][2] if body else last_relu_in, flags=flags)
+            if in_pad is not None and in_pad != x_id.shape[1]:
+                x_pair = K.Pair16.zeros(x_id.shape[0], in_pad, act_exp(), x_id.device)
+                K.split_f16(x_id, act_exp(), relu=body[0][2] if body else last_relu_in, out=x_pair.cols(0, x_id.shape[1]), flags=flags)
+            else:
+                x_pair = K.split_f16(x_id, act_exp(), relu=body[0][2] if body else last_relu_in, flags=flags)
+        elif in_pad is not None and in_pad != x_pair.shape[1]:
+            raise ValueError("a pre-split input of {} columns cannot feed an initial layer padded to {}".format(x_pair.shape[1], in_pad))
         elif (body[0][2] if body else last_relu_in):
             raise ValueError("a pre-split input cannot feed a layer that applies relu to its input")
         state = ChainState(pair=x_pair)
@@ -257,22 +344,50 @@ def _run_trunk_block(chain, x, id_cols, use_tc, last_out, x_pair, flags):
             scratch = torch.empty_like(y) if any(f & 4 for f in trunk_flags) else None
             K.residual_trunk(pair, w_hi, w_lo, exps, bias_all, trunk_flags, y, scratch, out, flags=flags)
             return ChainState(pair=out)
+        ctx_pair = chain.context_pair(flags) if isinstance(chain, Chain) else None
+        conv = getattr(chain, "conv3x3", ())
+        geom = current_geometry()
         for i, (weight, bias, relu_in, relu_out, residual) in enumerate(body):
-            need_raw = i + 2 < len(chain) and chain[i + 2][4] == "skip"
-            res = skip_src if residual == "skip" else None
-            y, pair = K.linear_f16x3(state.pair, split_weight(weight), bias.detach() if bias is not None else None,
-                                     residual=res, relu_out=relu_out, want_y=need_raw, want_split=True,
-                                     split_relu=chain[i + 1][2], pair_out=last_out if i == len(body) - 1 else None,
-                                     flags=flags)
+            if i in conv:       # 3x3 convolution: dense layer on the im2col of the (already activated) incoming pair
+                if geom is None or state.pair.shape[0] % (geom[1] * geom[2]):
+                    raise RuntimeError("a 3x3 convolution layer needs whole images (dense.image_geometry)")
+                state = ChainState(raw=state.raw, pair=K.im2col3x3(state.pair, state.pair.shape[0] // (geom[1] * geom[2]), geom[1], geom[2]))
+            need_raw = i + 2 < len(chain) and chain[i + 2][4] in ("skip", "glu_skip")
+            pair_out = last_out if i == len(body) - 1 else None
+            b = bias.detach() if bias is not None else None
+            if residual == "glu_skip":
+                # inputs + (W2 a + b2) * sigmoid(Wc context + bc): two GEMMs and one elementwise pass
+                wg, bg, _ = chain.ctx_gates[i]
+                gate = K.linear_f16x3(ctx_pair, split_weight(wg), bg.detach(), want_y=True, flags=flags)[0]
+                t = K.linear_f16x3(state.pair, split_weight(weight), b, relu_out=relu_out, want_y=True, flags=flags)[0]
+                y, pair = K.glu_skip(t, gate, skip_src, want_y=need_raw, want_split=True, split_relu=chain[i + 1][2],
+                                     pair_out=pair_out, flags=flags)
+            else:
+                res = skip_src if residual == "skip" else None
+                if residual == "ctx_init":          # [inputs, context] W0^T + b0 = inputs W0a^T + (context W0b^T + b0)
+                    wb, bb, _ = chain.ctx_init
+                    res = K.linear_f16x3(ctx_pair, split_weight(wb), bb.detach() if bb is not None else None, want_y=True,
+                                         flags=flags)[0]
+                y, pair = K.linear_f16x3(state.pair, split_weight(weight), b, residual=res, relu_out=relu_out, want_y=need_raw,
+                                         want_split=True, split_relu=chain[i + 1][2], pair_out=pair_out, flags=flags)
             if need_raw:
                 skip_src = y
             state = ChainState(raw=y, pair=pair)
         return state
     hidden = x if id_cols is None else K.gather_cols(x, id_cols)
     branch = None
-    for weight, bias, relu_in, relu_out, residual in body:
+    ctx = chain.context.contiguous() if isinstance(chain, Chain) else None
+    for i, (weight, bias, relu_in, relu_out, residual) in enumerate(body):
         b = bias.detach() if bias is not None else None
-        if residual == "skip":
+        if residual == "ctx_init":
+            _, bb, wb = chain.ctx_init
+            c0 = K.linear(ctx, wb, bb.detach() if bb is not None else None)
+            hidden = K.linear(hidden, weight.detach(), None, residual=c0, relu_in=relu_in, relu_out=relu_out)
+        elif residual == "glu_skip":
+            _, bg, wg = chain.ctx_gates[i]
+            t = K.linear(branch, weight.detach(), b, relu_in=relu_in, relu_out=relu_out)
+            hidden = K.glu_skip(t, K.linear(ctx, wg, bg.detach()), hidden, want_y=True)[0]
+        elif residual == "skip":
             hidden = K.linear(branch, weight.detach(), b, residual=hidden, relu_in=relu_in, relu_out=relu_out, out=hidden)
         elif relu_in:   # first layer of a residual block: keep its input for the skip connection
             branch = K.linear(hidden, weight.detach(), b, relu_in=True, relu_out=relu_out)

@@ -40,6 +40,34 @@ def affine_flow_2d(hidden_features=8):
                 StandardNormal([2]))
 
 
+def glow_multiscale(image_shape=(3, 32, 32), levels=4, steps=8, hidden_channels=96, num_bins=8, tail_bound=3.0):
+    """cfg 5: `levels` x [SqueezeTransform, `steps` x [ActNorm, OneByOneConvolution, RQ coupling over channels (mid-split mask
+    alternated with its complement, ConvResidualNet conditioner)]] combined by a MultiscaleCompositeTransform; same module tree
+    (state_dict keys) and RNG consumption as the same stack built from the reference's classes."""
+    import numpy as np
+    from ..nn.nets import ConvResidualNet
+    c, h, w = image_shape
+    mct = T.MultiscaleCompositeTransform(num_transforms=levels)
+    for _ in range(levels):
+        squeeze = T.SqueezeTransform()
+        c, h, w = squeeze.get_output_shape(c, h, w)
+        layers = [squeeze]
+        for i in range(steps):
+            mask = torchutils.create_mid_split_binary_mask(c)
+            if i % 2:
+                mask = 1 - mask
+            layers.append(T.CompositeTransform([
+                T.ActNorm(c), T.OneByOneConvolution(c),
+                T.PiecewiseRationalQuadraticCouplingTransform(
+                    mask=mask, transform_net_create_fn=lambda i_, o_: ConvResidualNet(i_, o_, hidden_channels=hidden_channels,
+                                                                                      num_blocks=2),
+                    num_bins=num_bins, tails="linear", tail_bound=tail_bound)]))
+        shape = mct.add_transform(T.CompositeTransform(layers), (c, h, w))
+        if shape is not None:
+            c, h, w = shape
+    return Flow(mct, StandardNormal([int(np.prod(image_shape))]))
+
+
 def perturb_(flow, seed=2):
     """The well-conditioned perturbation of SURVEY.md section 8d (makes ActNorm / LU / splines non-trivial)."""
     import numpy as np

@@ -232,6 +232,16 @@ class Pair16:
         return cls(torch.empty(rows, cols, dtype=torch.float16, device=device),
                    torch.empty(rows, cols, dtype=torch.float16, device=device), exp)
 
+    @classmethod
+    def zeros(cls, rows, cols, exp, device):
+        p = cls.empty(rows, cols, exp, device)
+        for t in (p.hi, p.lo):
+            if t.numel() and t.numel() % 2 == 0:
+                fill_(t.view(-1).view(torch.float32), 0.0)      # two fp16 zeros per fp32 zero
+            else:
+                t.zero_()
+        return p
+
     @property
     def shape(self):
         return self.hi.shape
@@ -271,6 +281,78 @@ def split_f16(x, exp, relu=False, out=None, flags=None):
         N.check(N.lib().nfk_split_f16(x.data_ptr(), x.stride(0), c, int(relu), int(exp), pair.hi.data_ptr(), pair.lo.data_ptr(),
                                       pair.hi.stride(0), n, N.ptr(flags), N.stream()))
     return pair
+
+
+def glu_skip(t, gate, skip=None, want_y=True, want_split=False, split_relu=False, split_exp=None, pair_out=None, flags=None):
+    """skip + t * sigmoid(gate) (the context gate of a residual block, nn/nets/resnet.py:50-53) in one pass.
+    Returns (y fp32 or None, Pair16 of pre(y) or None)."""
+    _rows2d(t, "t"); _rows2d(gate, "gate")
+    n, c = t.shape
+    y = torch.empty(n, c, dtype=torch.float32, device=t.device) if want_y else None
+    pair = None
+    if want_split:
+        from . import config
+        exp = config.activation_exp if split_exp is None else split_exp
+        pair = pair_out if pair_out is not None else Pair16.empty(n, c, exp, t.device)
+    with timed("glu_skip_%d" % c, n):
+        N.check(N.lib().nfk_glu_skip_rows(
+            t.data_ptr(), t.stride(0), gate.data_ptr(), gate.stride(0), N.ptr(skip), skip.stride(0) if skip is not None else 0,
+            N.ptr(y), y.stride(0) if y is not None else 0, pair.hi.data_ptr() if pair else 0, pair.lo.data_ptr() if pair else 0,
+            pair.hi.stride(0) if pair else 0, pair.exp if pair else 0, int(split_relu), n, c, N.ptr(flags), N.stream()))
+    return y, pair
+
+
+# ---- image path: pixel rows (include/nfk.h, "image path") ----------------------------------------------------------------
+def nchw_to_rows(x):
+    """[B, C, H, W] fp32 -> pixel rows [B*H*W, C]."""
+    b, c, h, w = x.shape
+    x = x.contiguous()
+    rows = torch.empty(b * h * w, c, dtype=torch.float32, device=x.device)
+    with timed("nchw_to_rows", b * h * w):
+        N.check(N.lib().nfk_nchw_to_rows(x.data_ptr(), rows.data_ptr(), b, c, h * w, 0, N.stream()))
+    return rows
+
+
+def rows_to_nchw(rows, b, c, h, w):
+    out = torch.empty(b, c, h, w, dtype=torch.float32, device=rows.device)
+    rows = rows.contiguous()
+    with timed("rows_to_nchw", b * h * w):
+        N.check(N.lib().nfk_nchw_to_rows(rows.data_ptr(), out.data_ptr(), b, c, h * w, 1, N.stream()))
+    return out
+
+
+def squeeze_rows(rows, b, c, h, w, inverse=False):
+    """SqueezeTransform(2) on pixel rows of a [b, c, h, w] image; returns (rows, (c, h, w)) of the result."""
+    rows = rows.contiguous()
+    if not inverse:
+        if h % 2 or w % 2:
+            raise ValueError("Input image size not compatible with the factor.")
+        out = torch.empty(b * (h // 2) * (w // 2), 4 * c, dtype=torch.float32, device=rows.device)
+        N.check(N.lib().nfk_squeeze_rows(rows.data_ptr(), out.data_ptr(), b, h // 2, w // 2, c, 0, N.stream()))
+        return out, (4 * c, h // 2, w // 2)
+    if c < 4 or c % 4:
+        raise ValueError("Invalid number of channel dimensions.")
+    out = torch.empty(b * h * w * 4, c // 4, dtype=torch.float32, device=rows.device)
+    N.check(N.lib().nfk_squeeze_rows(rows.data_ptr(), out.data_ptr(), b, h, w, c // 4, 1, N.stream()))
+    return out, (c // 4, 2 * h, 2 * w)
+
+
+def im2col3x3(pair, n_images, h, w):
+    """Pair16 [n_images*h*w, C] -> Pair16 [n_images*h*w, 9*C]: the operand of a 3x3 / padding-1 convolution as a dense layer."""
+    n, c = pair.shape
+    if n != n_images * h * w:
+        raise ValueError("{} rows are not {} images of {}x{} pixels".format(n, n_images, h, w))
+    out = Pair16.empty(n, 9 * c, pair.exp, pair.hi.device)
+    with timed("im2col3x3_%d" % c, n):
+        N.check(N.lib().nfk_im2col3x3_f16(pair.hi.data_ptr(), pair.lo.data_ptr(), pair.hi.stride(0), out.hi.data_ptr(), out.lo.data_ptr(),
+                                          out.hi.stride(0), n_images, h, w, c, N.stream()))
+    return out
+
+
+def segment_sum_(values, out_accum, segment_len):
+    """out_accum[s] += sum(values[s*segment_len : (s+1)*segment_len])."""
+    N.check(N.lib().nfk_segment_sum(values.data_ptr(), out_accum.data_ptr(), out_accum.numel(), int(segment_len), N.stream()))
+    return out_accum
 
 
 def f16x3_supported(lda, ldw, in_features):

@@ -106,9 +106,76 @@ class CompositeTransform(Transform):
         return outputs, total
 
     def _native_ready(self, inputs, context):
-        return K.native_ok(inputs, context) and inputs.dim() == 2 and params_frozen(self)
+        if not (K.native_ok(inputs, context) and params_frozen(self)):
+            return False
+        return inputs.dim() == 2 or (inputs.dim() == 4 and self._image_ready(inputs, context))
+
+    # ---- image chains: [B, C, H, W] inputs run as PIXEL ROWS [B*H*W, C] through the 2-D machinery ---------------------------
+    def _image_ready(self, inputs, context):
+        """Every leaf has a per-pixel form: ActNorm, OneByOneConvolution, SqueezeTransform(2) and RQ couplings over channels with
+        a ConvResidualNet the dense path can run (BASELINE cfg 5).  Anything else: torch path."""
+        from .. import dense as D
+        from .conv import OneByOneConvolution
+        from .coupling import PiecewiseRationalQuadraticCouplingTransform
+        from .normalization import ActNorm
+        from .reshape import SqueezeTransform
+        if context is not None or D.backend() != "tc":
+            return False
+        b, c, h, w = inputs.shape
+        for leaf, _ in _flatten(self, False, []):
+            if type(leaf) is SqueezeTransform:
+                if leaf.factor != 2:
+                    return False
+            elif type(leaf) is ActNorm:
+                if leaf.training and not bool(leaf.initialized):
+                    return False
+            elif type(leaf) is OneByOneConvolution:
+                pass
+            elif type(leaf) is PiecewiseRationalQuadraticCouplingTransform:
+                net = leaf.transform_net
+                with D.image_geometry(1, 2, 2):
+                    chain = net.dense_chain(None) if (leaf.unconditional_transform is None and hasattr(net, "dense_chain")) else None
+                    if not isinstance(chain, D.ConvChain) or not D.chain_uses_tc(chain, leaf.num_identity_features) \
+                            or not leaf._fused_final_ready(chain):
+                        return False
+            else:
+                return False
+        return True
+
+    def _native_apply_image(self, inputs, lad, flags, inverse):
+        """Layout change at the ends, SqueezeTransforms as row gathers, everything between them as a 2-D chain on the pixel rows
+        with a per-PIXEL log|det| buffer that is folded into the per-sample one (sum over H, W) whenever the pixel grid changes."""
+        from .. import dense as D
+        from .reshape import SqueezeTransform
+        b, c, h, w = inputs.shape
+        rows = K.nchw_to_rows(inputs)
+        segment = []
+
+        def flush(rows):
+            if not segment:
+                return rows
+            lad_pix = K.fill_(torch.empty(b * h * w, dtype=torch.float32, device=rows.device), 0.0)
+            with D.image_geometry(b, h, w):
+                rows = self._run_leaves(list(segment), rows, lad_pix, flags, None)
+            K.segment_sum_(lad_pix, lad, h * w)
+            segment.clear()
+            return rows
+
+        for leaf, inv in _flatten(self, inverse, []):
+            if type(leaf) is SqueezeTransform:
+                rows = flush(rows)
+                rows, (c, h, w) = K.squeeze_rows(rows, b, c, h, w, inverse=inv)
+            else:
+                segment.append((leaf, inv))
+        rows = flush(rows)
+        return K.rows_to_nchw(rows, b, c, h, w)
 
     def _native_apply(self, inputs, lad, flags, inverse, context=None):
+        if inputs.dim() == 4:
+            return self._native_apply_image(inputs, lad, flags, inverse)
+        return self._run_leaves(_flatten(self, inverse, []), inputs, lad, flags, context)
+
+    def _run_leaves(self, leaves, inputs, lad, flags, context=None):
         """Walks the flattened leaves.  Between leaves the tensor may live in a permuted COLUMN LAYOUT (fused_affine.Layout):
         a coupling that runs on the fused tensor-core path asks for its identity features first / transformed features
         last; the folded affine run in front of it emits that order for free (a row permutation of its weight matrix) and
@@ -116,7 +183,6 @@ class CompositeTransform(Transform):
         between layers.  Leaves that know nothing about layouts always see the logical column order."""
         from .fused_affine import AffineRun, is_affine_leaf
 
-        leaves = _flatten(self, inverse, [])
         x = inputs
         layout = None            # None = logical column order
         owned = False            # x is a temporary of this chain (may be overwritten in place)
@@ -135,7 +201,7 @@ class CompositeTransform(Transform):
             j = i
             has_lu = False
             while j < len(leaves) and is_affine_leaf(leaves[j][0], x):
-                has_lu = has_lu or leaves[j][0].__class__.__name__ in ("LULinear",)
+                has_lu = has_lu or leaves[j][0].__class__.__name__ in ("LULinear", "OneByOneConvolution")
                 j += 1
             if has_lu and j - i >= 1:
                 run = AffineRun.cached(self._affine_cache, leaves[i:j], x.device)
@@ -147,7 +213,7 @@ class CompositeTransform(Transform):
                 if out_layout is not None and config.fused_pair_only and pair_cols % 8 == 0:
                     k, lu_next = j + 1, False
                     while k < len(leaves) and is_affine_leaf(leaves[k][0], x):
-                        lu_next = lu_next or leaves[k][0].__class__.__name__ in ("LULinear",)
+                        lu_next = lu_next or leaves[k][0].__class__.__name__ in ("LULinear", "OneByOneConvolution")
                         k += 1
                     if lu_next:
                         y_first_col = pair_cols
@@ -169,7 +235,7 @@ class CompositeTransform(Transform):
                 k = i + 1
                 lu_next = False
                 while k < len(leaves) and is_affine_leaf(leaves[k][0], x):
-                    lu_next = lu_next or leaves[k][0].__class__.__name__ in ("LULinear",)
+                    lu_next = lu_next or leaves[k][0].__class__.__name__ in ("LULinear", "OneByOneConvolution")
                     k += 1
                 carry["pair_only"] = lu_next
                 x = leaf._native_apply(x, lad, flags, inv, context, layout=layout, owned=owned, carry=carry)

@@ -142,7 +142,7 @@ class CouplingTransform(Transform):
         if pair is None:
             pair = K.Pair16.empty(n, self.features, D.act_exp(), x.device)
             K.split_f16(x[:, :d_id], pair.exp, out=pair.cols(0, d_id), flags=flags)
-        block = max(128, int(config.coupling_block_rows))
+        block = D.whole_images(max(128, int(config.coupling_block_rows)))
         use_step = self._step_ready(chain)
         for r0 in range(0, n, block):
             r1 = min(n, r0 + block)
@@ -153,7 +153,7 @@ class CouplingTransform(Transform):
                                  None if pair_only else xs, lad[r0:r1], flags, inverse,
                                  y_pair=pair.rows(r0, r1) if pair_only else None)
                 continue
-            state = D.run_trunk(chain, xs, None, True, x_pair=pair.cols(0, d_id).rows(r0, r1), flags=flags)
+            state = D.run_trunk(D.chain_rows(chain, r0, r1), xs, None, True, x_pair=pair.cols(0, d_id).rows(r0, r1), flags=flags)
             with K.timed("rq_coupling_final", r1 - r0):
                 if pair_only:
                     self._fused_final(chain, state, xs, (d_id, self.features - d_id), None, lad[r0:r1], flags, inverse,
@@ -198,7 +198,7 @@ class CouplingTransform(Transform):
         net = self.transform_net
         chain = net.dense_chain(context) if hasattr(net, "dense_chain") else None
         n_params = self.num_transform_features * self._transform_dim_multiplier()
-        trunk_rows = 1 << 15
+        trunk_rows = D.whole_images(1 << 15)
         use_tc = chain is not None and D.chain_uses_tc(chain, self.num_identity_features)
         final_rows = self._conditioner_rows(n_params)
         if use_tc and self._fused_final_ready(chain):
@@ -214,10 +214,10 @@ class CouplingTransform(Transform):
             if self._all_cols is None or self._all_cols.device != inputs.device:
                 self._all_cols = torch.arange(self.features, dtype=torch.int32, device=inputs.device)
             K.gather_cols(inputs, self._all_cols, out=outputs)
-            block = max(128, int(config.coupling_block_rows))
+            block = D.whole_images(max(128, int(config.coupling_block_rows)))
             for r0 in range(0, n, block):
                 r1 = min(n, r0 + block)
-                state = D.run_trunk(chain, inputs[r0:r1], id_cols, True, flags=flags)
+                state = D.run_trunk(D.chain_rows(chain, r0, r1), inputs[r0:r1], id_cols, True, flags=flags)
                 with K.timed("rq_coupling_final", r1 - r0):
                     self._fused_final(chain, state, outputs[r0:r1], t_cols, outputs[r0:r1], lad[r0:r1], flags, inverse)
             return outputs
@@ -236,7 +236,7 @@ class CouplingTransform(Transform):
                 self._native_epilogue(xs, params.float().contiguous(), t_cols, id_cols, outputs[r0:r1], lad[r0:r1], flags,
                                       inverse)
                 continue
-            state = D.run_trunk(chain, xs, id_cols, use_tc, flags=flags)
+            state = D.run_trunk(D.chain_rows(chain, r0, r1), xs, id_cols, use_tc, flags=flags)
             for q0 in range(0, r1 - r0, final_rows):
                 q1 = min(r1 - r0, q0 + final_rows)
                 with K.timed("final_linear", q1 - q0):

@@ -32,6 +32,7 @@ class Layout:
 
 
 def is_affine_leaf(leaf, x):
+    from .conv import OneByOneConvolution
     from .lu import LULinear
     from .normalization import ActNorm
     from .permutations import Permutation, RandomPermutation, ReversePermutation
@@ -43,6 +44,10 @@ def is_affine_leaf(leaf, x):
         return x.dim() == 2 and not (leaf.training and not bool(leaf.initialized))
     if type(leaf) in (Permutation, RandomPermutation, ReversePermutation):
         return leaf._dim == 1
+    if type(leaf) is OneByOneConvolution:
+        # on pixel rows (native image chain, dense.image_geometry) Glow's 1x1 convolution IS a channel permutation followed by
+        # an LULinear of every row (conv.py:17-29 of the reference)
+        return D.current_geometry() is not None and x.dim() == 2
     return type(leaf) is LULinear
 
 
@@ -69,7 +74,17 @@ class AffineRun:
         A = np.eye(d, dtype=np.float64)
         c = np.zeros(d, dtype=np.float64)
         lad = 0.0
+        from .conv import OneByOneConvolution
+
+        def permute(A, c, leaf, inv):
+            perm = leaf._permutation.detach().cpu().numpy()
+            if inv:
+                perm = np.argsort(perm, kind="stable")
+            return A[perm, :], c[perm]
+
         for leaf, inv in leaves:
+            if isinstance(leaf, OneByOneConvolution) and not inv:      # forward: the convolution's own permutation first
+                A, c = permute(A, c, leaf.permutation, False)
             if isinstance(leaf, ActNorm):
                 log_s = leaf.log_scale.detach().double().cpu().numpy()
                 t = leaf.shift.detach().double().cpu().numpy()
@@ -97,11 +112,9 @@ class AffineRun:
                     c = lower @ (upper @ c) + b
                     lad += np.log(diag).sum()
             else:  # Permutation
-                perm = leaf._permutation.detach().cpu().numpy()
-                if inv:
-                    perm = np.argsort(perm, kind="stable")
-                A = A[perm, :]
-                c = c[perm]
+                A, c = permute(A, c, leaf, inv)
+            if isinstance(leaf, OneByOneConvolution) and inv:          # inverse: LU^-1, then the permutation's inverse
+                A, c = permute(A, c, leaf.permutation, True)
         self._A, self._c, self._device = A, c, device
         self._operands = {}
         self.weight, self.bias = self.operands(None, None)

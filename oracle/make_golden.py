@@ -354,8 +354,63 @@ def context_rows():
     save("context_rows", rec)
 
 
+def glow_multiscale(image_shape=(3, 16, 16), levels=3, steps=2, hidden_channels=32, num_bins=8, tail_bound=3.0):
+    """BASELINE cfg 5 in small: `levels` x [SqueezeTransform, `steps` x [ActNorm, OneByOneConvolution, RQ coupling over channels
+    (mid-split mask alternated with its complement, ConvResidualNet conditioner)]] under a MultiscaleCompositeTransform."""
+    from nflows.nn.nets import ConvResidualNet
+    c, h, w = image_shape
+    mct = T.MultiscaleCompositeTransform(num_transforms=levels)
+    for _ in range(levels):
+        squeeze = T.SqueezeTransform()
+        c, h, w = squeeze.get_output_shape(c, h, w)
+        layers = [squeeze]
+        for i in range(steps):
+            mask = torchutils.create_mid_split_binary_mask(c)
+            if i % 2:
+                mask = 1 - mask
+            layers.append(T.CompositeTransform([
+                T.ActNorm(c), T.OneByOneConvolution(c),
+                T.PiecewiseRationalQuadraticCouplingTransform(
+                    mask=mask, transform_net_create_fn=lambda i_, o_: ConvResidualNet(i_, o_, hidden_channels=hidden_channels, num_blocks=2),
+                    num_bins=num_bins, tails="linear", tail_bound=tail_bound)]))
+        shape = mct.add_transform(T.CompositeTransform(layers), (c, h, w))
+        if shape is not None:
+            c, h, w = shape
+    return Flow(mct, StandardNormal([int(np.prod(image_shape))]))
+
+
+def image_rows():
+    """Round 2: the image path (BASELINE cfg 5 in small): 3 x 16 x 16 images, 3 levels x 2 steps, 32 hidden
+    channels -- squeezed channel counts 12 / 24 / 48, i.e. 6 / 12 / 24 identity channels (padded and unpadded initial layers,
+    gathered and packed coupling paths)."""
+    rec = {}
+    with torch.no_grad():
+        torch.manual_seed(30)
+        flow = glow_multiscale().eval()
+        perturb(flow)
+        g = torch.Generator().manual_seed(31)
+        for name, p in flow.named_parameters():          # the zero-initialised 3x3 convolutions must matter in the outputs
+            if "conv_layers" in name and name.endswith("weight"):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+        x = torch.randn(6, 3, 16, 16)
+        z = flow.transform_to_noise(x)
+        lp = flow.log_prob(x)
+        lp64 = flow.double().log_prob(x.double())
+        z64 = flow.transform_to_noise(x.double())
+        flow.float()
+        noise = torch.randn(6, 3 * 16 * 16)
+        xs, lad_inv = flow._transform.inverse(noise)
+        xs64, lad_inv64 = flow.double()._transform.inverse(noise.double())
+        flow.float()
+        rec["glow_small"] = dict(sd=flow.state_dict(), x=x, z=z, z_fp64=z64, log_prob=lp, log_prob_fp64=lp64, noise=noise, sample=xs,
+                                 sample_fp64=xs64, lad_inv=lad_inv, lad_inv_fp64=lad_inv64)
+    save("image_rows", rec)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "next_rows":
+    if len(sys.argv) > 1 and sys.argv[1] == "image_rows":
+        image_rows()
+    elif len(sys.argv) > 1 and sys.argv[1] == "next_rows":
         next_rows()
     elif len(sys.argv) > 1 and sys.argv[1] == "context_rows":
         context_rows()
@@ -363,3 +418,4 @@ if __name__ == "__main__":
         main()
         next_rows()
         context_rows()
+        image_rows()

@@ -182,3 +182,17 @@ def test_next_rows_cpu_replay_of_reference_goldens():
         warnings.simplefilter("ignore")
         y, lad = t(r["x"])
     assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= TOL
+
+
+@torch.no_grad()
+def test_image_flow_cpu_replay_of_reference_golden():
+    """tests/golden/image_rows.pt (BASELINE cfg 5 in small, reference outputs): recipes.glow_multiscale has the reference's module
+    tree (strict state_dict load) and the package's CPU path reproduces log_prob, the noise and the inverse."""
+    from nflows_b200.flows import recipes
+    g = load_golden("image_rows")["glow_small"]
+    flow = recipes.glow_multiscale(image_shape=(3, 16, 16), levels=3, steps=2, hidden_channels=32).eval()
+    flow.load_state_dict(g["sd"], strict=True)
+    assert rel_err(flow.log_prob(g["x"]), g["log_prob"]) <= TOL
+    assert rel_err(flow.transform_to_noise(g["x"]), g["z"]) <= TOL
+    xs, lad = flow._transform.inverse(g["noise"])
+    assert rel_err(xs, g["sample"]) <= 1e-4 and rel_err(lad, g["lad_inv"]) <= 1e-4

@@ -536,8 +536,9 @@ def test_next_rows_against_reference_goldens(cuda_device):
 @torch.no_grad()
 def test_context_conditioned_flow_against_reference_golden(cuda_device):
     """Flow with an embedding net and context-conditioned ResidualNet conditioners (GLU gates) -- reference
-    outputs in tests/golden/context_rows.pt.  The folded affine runs and the spline epilogue run on our kernels; the gated
-    conditioner itself is evaluated by torch on the GPU (dense_chain() declines a context)."""
+    outputs in tests/golden/context_rows.pt.  Everything below the embedding net runs on our kernels: the folded affine runs,
+    the gated conditioner (dense.Chain: context projection added to the initial layer, nfk_glu_skip_rows behind every block)
+    and the fused final layer + spline."""
     from nflows_b200.distributions.normal import StandardNormal
     from nflows_b200.flows import Flow
     g = load_golden("context_rows")["context_flow"]
@@ -554,10 +555,23 @@ def test_context_conditioned_flow_against_reference_golden(cuda_device):
     flow.load_state_dict(g["sd"], strict=True)
     flow = flow.to(cuda_device)
     x, c = g["x"].to(cuda_device), g["context"].to(cuda_device)
-    with native_launches():
-        lp = flow.log_prob(x, context=c)
+    K.TIMELINE = []
+    try:
+        with native_launches():
+            lp = flow.log_prob(x, context=c)
+        tags = {t[0] for t in K.TIMELINE}
+    finally:
+        K.TIMELINE = None
+    assert any(t.startswith("glu_skip_") for t in tags) and "rq_coupling_final" in tags, tags     # the gated conditioner ran natively
     assert rel_err(lp.cpu(), g["log_prob_fp64"]) <= max(TOL, 3 * rel_err(g["log_prob"], g["log_prob_fp64"]))
     assert rel_err(flow.transform_to_noise(x, context=c).cpu(), g["z"]) <= 5e-5
+    # FFMA dense layers (NFLOWS_B200_GEMM=simt route of the same chain) agree
+    import os
+    os.environ["NFLOWS_B200_GEMM"] = "simt"
+    try:
+        assert rel_err(flow.log_prob(x, context=c).cpu(), g["log_prob_fp64"]) <= max(TOL, 3 * rel_err(g["log_prob"], g["log_prob_fp64"]))
+    finally:
+        os.environ.pop("NFLOWS_B200_GEMM")
     xs, _ = flow._transform.inverse(g["noise"].to(cuda_device), context=flow._embedding_net(c))
     assert rel_err(xs.cpu(), g["sample"]) <= 1e-3          # 3 spline inverses in a row: the reference's own round trip is ~1e-3
     assert flow.sample(4, context=c[:5]).shape == (5, 4, features)
