@@ -253,6 +253,26 @@ def extra_workloads(dev, flow):
                                           "forward_samples_per_s": (1 << 18) / (ms_f * 1e-3)}
         except Exception as exc:
             out["cfg4_ar_rq_D64_2^18"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+        try:
+            # cfg 5: Glow-style multiscale flow on 3x32x32 images (4 levels x 8 steps, 96 hidden channels), native pixel-row chain;
+            # beside it the same flow as eager PyTorch (cuDNN convolutions) on this GPU, fp64 inputs never take the native path
+            torch.manual_seed(0)
+            glow = recipes.perturb_(recipes.glow_multiscale()).eval().to(dev)
+            n = 512
+            img = torch.randn(n, 3, 32, 32, device=dev)
+            ms_lp = timed(lambda: glow.log_prob(img), iters=3, warm=2)
+            ms_s = timed(lambda: glow.sample(n), iters=3, warm=2)
+            rec = {"images": n, "log_prob_ms": ms_lp, "log_prob_images_per_s": n / (ms_lp * 1e-3), "sample_ms": ms_s,
+                   "sample_images_per_s": n / (ms_s * 1e-3)}
+            with torch.enable_grad():           # autograd on = the differentiable torch formulation of the same modules
+                ms_eager = timed(lambda: glow.log_prob(img).detach(), iters=2, warm=1)
+            rec["torch_eager_same_gpu_log_prob_ms"] = ms_eager
+            want = glow.double().log_prob(img[:32].double()).float()
+            got = glow.float().log_prob(img[:32])
+            rec["log_prob_rel_err_vs_fp64"] = float(((got - want).abs() / torch.maximum(want.abs(), torch.ones_like(want))).max())
+            out["cfg5_glow_3x32x32"] = rec
+        except Exception as exc:
+            out["cfg5_glow_3x32x32"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
     return out
 
 

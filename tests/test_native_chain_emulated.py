@@ -1,0 +1,88 @@
+"""Host logic of the native execution chain -- column layouts, row blocking, context chains, the pixel-row image driver -- run
+on the CPU with the kernel wrappers replaced by torch restatements of their contracts (tests/emulated_kernels.py).  What is
+under test is everything ABOVE the C ABI; the kernels themselves are checked on hardware by the `-m gpu` tests."""
+import pytest
+import torch
+
+import emulated_kernels
+from conftest import load_golden, rel_err
+from nflows_b200 import config
+from nflows_b200 import transforms as T
+from nflows_b200.flows import recipes
+
+TOL = 1e-5
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    monkeypatch.setattr(config, "coupling_step_kernel", False)
+    return emulated_kernels.install(monkeypatch)
+
+
+@torch.no_grad()
+def test_small_nsf_flow_through_the_native_chain(emu):
+    """The emulation itself: a cfg-3-shaped flow (folded affine runs, packed couplings, pair hand-off) equals the torch path."""
+    torch.manual_seed(0)
+    flow = recipes.perturb_(recipes.rq_nsf(32, hidden_features=32, num_layers=3)).eval()
+    x = torch.randn(300, 32)
+    want = [t.float() for t in flow.double()._transform(x.double())]          # fp64 inputs always take the torch formulation
+    flow.float()
+    config.coupling_block_rows, saved = 128, config.coupling_block_rows
+    try:
+        got = flow._transform(x)
+    finally:
+        config.coupling_block_rows = saved
+    assert emu.get("rq_coupling_final", 0) == 9 and emu.get("linear_f16x3", 0) > 0            # 3 couplings x 3 row blocks
+    assert rel_err(got[0], want[0]) <= TOL and rel_err(got[1], want[1]) <= TOL
+    back = flow._transform.inverse(want[0])
+    assert rel_err(back[0], x) <= 1e-4
+
+
+@torch.no_grad()
+def test_context_flow_through_the_native_chain(emu):
+    """the reference golden of the context-conditioned flow through dense.Chain (ctx_init / glu_skip)."""
+    from nflows_b200.distributions.normal import StandardNormal
+    from nflows_b200.flows import Flow
+    from nflows_b200.nn.nets import ResidualNet
+    from nflows_b200.utils import torchutils
+    g = load_golden("context_rows")["context_flow"]
+    features, ctx_raw, ctx = 16, 5, 6
+    steps = []
+    for i in range(3):
+        steps.append(T.ActNorm(features))
+        steps.append(T.CompositeTransform([T.RandomPermutation(features), T.LULinear(features, identity_init=True)]))
+        steps.append(T.PiecewiseRationalQuadraticCouplingTransform(
+            mask=torchutils.create_alternating_binary_mask(features, even=(i % 2 == 0)),
+            transform_net_create_fn=lambda i_, o_: ResidualNet(i_, o_, hidden_features=32, context_features=ctx, num_blocks=2),
+            num_bins=8, tails="linear", tail_bound=3.0))
+    flow = Flow(T.CompositeTransform(steps), StandardNormal([features]), embedding_net=torch.nn.Linear(ctx_raw, ctx)).eval()
+    flow.load_state_dict(g["sd"], strict=True)
+    config.coupling_block_rows, saved = 128, config.coupling_block_rows      # 300 rows: three row blocks, context sliced alike
+    try:
+        lp = flow.log_prob(g["x"], context=g["context"])
+    finally:
+        config.coupling_block_rows = saved
+    assert emu.get("glu_skip", 0) == 3 * 2 * 3                               # 3 couplings x 2 blocks x 3 row blocks
+    assert rel_err(lp, g["log_prob_fp64"]) <= max(TOL, 3 * rel_err(g["log_prob"], g["log_prob_fp64"]))
+
+
+@torch.no_grad()
+def test_image_flow_through_the_pixel_row_chain(emu):
+    """the reference golden of the small Glow-style flow through CompositeTransform._native_apply_image --
+    NCHW <-> pixel rows, squeeze on rows, OneByOneConvolution folded into the affine run, ConvChain (padded initial layer, im2col
+    3x3 layers) + fused final layer, per-pixel log|det| folded per sample, forward and inverse."""
+    g = load_golden("image_rows")["glow_small"]
+    flow = recipes.glow_multiscale(image_shape=(3, 16, 16), levels=3, steps=2, hidden_channels=32).eval()
+    flow.load_state_dict(g["sd"], strict=True)
+    level = flow._transform._transforms[0]
+    assert level._native_ready(g["x"], None)
+    z, lad = flow._transform(g["x"])
+    assert emu.get("nchw_to_rows", 0) == 3 and emu.get("squeeze_rows", 0) == 3 and emu.get("im2col3x3", 0) == 3 * 2 * 4
+    # the two 12-channel affine folds (ActNorm + 1x1 convolution of level 1) are 12x12 maps: FFMA dense layer, K is no TMA row
+    assert emu.get("rq_coupling_final", 0) == 6 and emu.get("linear", 0) == 2
+    assert rel_err(z, g["z_fp64"]) <= max(TOL, 3 * rel_err(g["z"], g["z_fp64"]))
+    lp = flow.log_prob(g["x"])
+    assert rel_err(lp, g["log_prob_fp64"]) <= max(TOL, 3 * rel_err(g["log_prob"], g["log_prob_fp64"]))
+    xs, lad_inv = flow._transform.inverse(g["noise"])
+    assert rel_err(xs, g["sample_fp64"]) <= max(1e-4, 3 * rel_err(g["sample"], g["sample_fp64"]))
+    assert rel_err(lad_inv, g["lad_inv_fp64"]) <= max(1e-4, 3 * rel_err(g["lad_inv"], g["lad_inv_fp64"]))

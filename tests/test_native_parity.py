@@ -665,3 +665,35 @@ def test_flow_on_inputs_of_large_magnitude_matches_the_oracle(cuda_device):
         with native_launches():
             got = flow.log_prob(x.to(cuda_device))
     assert rel_err(got.cpu(), want) <= TOL
+
+
+@pytest.mark.gpu
+@torch.no_grad()
+def test_image_flow_against_reference_golden(cuda_device):
+    """SURVEY section 8 row f3 / BASELINE cfg 5 in small (tests/golden/image_rows.pt, reference outputs): Glow-style multiscale
+    flow on 3x16x16 images.  Every level runs as a pixel-row chain on our kernels -- layout change, squeeze gather, folded
+    ActNorm + 1x1 convolution, ConvResidualNet as dense layers (im2col of the fp16 pair for the 3x3 convolutions), fused final
+    layer + spline, per-sample log|det| -- forward, log_prob and inverse."""
+    g = load_golden("image_rows")["glow_small"]
+    flow = recipes.glow_multiscale(image_shape=(3, 16, 16), levels=3, steps=2, hidden_channels=32).eval()
+    flow.load_state_dict(g["sd"], strict=True)
+    flow = flow.to(cuda_device)
+    x = g["x"].to(cuda_device)
+    K.TIMELINE = []
+    try:
+        with native_launches():
+            z, lad = flow._transform(x)
+        tags = {t[0] for t in K.TIMELINE}
+    finally:
+        K.TIMELINE = None
+    assert {"nchw_to_rows", "rows_to_nchw", "im2col3x3_32", "rq_coupling_final"} <= tags, tags
+    assert rel_err(z.cpu(), g["z_fp64"]) <= max(TOL, 3 * rel_err(g["z"], g["z_fp64"]))
+    lp = flow.log_prob(x)
+    assert rel_err(lp.cpu(), g["log_prob_fp64"]) <= max(TOL, 3 * rel_err(g["log_prob"], g["log_prob_fp64"]))
+    xs, lad_inv = flow._transform.inverse(g["noise"].to(cuda_device))
+    assert rel_err(xs.cpu(), g["sample_fp64"]) <= max(1e-4, 3 * rel_err(g["sample"], g["sample_fp64"]))
+    assert rel_err(lad_inv.cpu(), g["lad_inv_fp64"]) <= max(1e-4, 3 * rel_err(g["lad_inv"], g["lad_inv_fp64"]))
+    # batch split consistency: images are independent
+    lp2 = torch.cat([flow.log_prob(x[:2]), flow.log_prob(x[2:])])
+    assert rel_err(lp2.cpu(), lp.cpu()) <= 1e-6
+    assert flow.sample(3).shape == (3, 3 * 16 * 16)
