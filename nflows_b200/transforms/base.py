@@ -204,7 +204,8 @@ class CompositeTransform(Transform):
                 has_lu = has_lu or leaves[j][0].__class__.__name__ in ("LULinear", "OneByOneConvolution")
                 j += 1
             if has_lu and j - i >= 1:
-                run = AffineRun.cached(self._affine_cache, leaves[i:j], x.device)
+                from .. import dense as D
+                run = AffineRun.cached(self._affine_cache, leaves[i:j], x.device, conv_pixels=D.current_geometry() is not None)
                 out_layout = wanted(j)
                 pair_cols = leaves[j][0].num_identity_features if out_layout is not None else 0
                 # the fp32 values of the identity block are never read when the coupling behind this run hands ONLY the fp16 pair

@@ -60,7 +60,10 @@ def _signature(leaves):
 
 
 class AffineRun:
-    def __init__(self, leaves, device):
+    def __init__(self, leaves, device, conv_pixels=False):
+        """conv_pixels: an OneByOneConvolution leaf stands for the whole 1x1 convolution on pixel rows (its channel
+        permutation AND its LU map -- native image chains); otherwise it is the bare LULinear it inherits from (its own
+        forward applies the permutation around the call, conv.py)."""
         from .lu import LULinear
         from .normalization import ActNorm
 
@@ -83,7 +86,7 @@ class AffineRun:
             return A[perm, :], c[perm]
 
         for leaf, inv in leaves:
-            if isinstance(leaf, OneByOneConvolution) and not inv:      # forward: the convolution's own permutation first
+            if conv_pixels and isinstance(leaf, OneByOneConvolution) and not inv:      # forward: its own permutation first
                 A, c = permute(A, c, leaf.permutation, False)
             if isinstance(leaf, ActNorm):
                 log_s = leaf.log_scale.detach().double().cpu().numpy()
@@ -113,7 +116,7 @@ class AffineRun:
                     lad += np.log(diag).sum()
             else:  # Permutation
                 A, c = permute(A, c, leaf, inv)
-            if isinstance(leaf, OneByOneConvolution) and inv:          # inverse: LU^-1, then the permutation's inverse
+            if conv_pixels and isinstance(leaf, OneByOneConvolution) and inv:          # inverse: LU^-1, then the permutation's inverse
                 A, c = permute(A, c, leaf.permutation, True)
         self._A, self._c, self._device = A, c, device
         self._operands = {}
@@ -137,12 +140,12 @@ class AffineRun:
         return hit[0], hit[1]
 
     @classmethod
-    def cached(cls, cache, leaves, device):
-        sig = (_signature(leaves), str(device), D.cache_epoch())
+    def cached(cls, cache, leaves, device, conv_pixels=False):
+        sig = (_signature(leaves), str(device), D.cache_epoch(), conv_pixels)
         key = tuple((id(leaf), inv) for leaf, inv in leaves)
         hit = cache.get(key)
         if hit is None or hit[0] != sig:
-            hit = (sig, cls(leaves, device))
+            hit = (sig, cls(leaves, device, conv_pixels))
             cache[key] = hit
         return hit[1]
 

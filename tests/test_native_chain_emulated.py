@@ -86,3 +86,19 @@ def test_image_flow_through_the_pixel_row_chain(emu):
     xs, lad_inv = flow._transform.inverse(g["noise"])
     assert rel_err(xs, g["sample_fp64"]) <= max(1e-4, 3 * rel_err(g["sample"], g["sample_fp64"]))
     assert rel_err(lad_inv, g["lad_inv_fp64"]) <= max(1e-4, 3 * rel_err(g["lad_inv"], g["lad_inv_fp64"]))
+
+
+@torch.no_grad()
+def test_standalone_one_by_one_convolution_through_the_native_chain(emu):
+    """OneByOneConvolution called on its own (4-D input, reference golden next_rows.pt): its forward applies the channel
+    permutation itself and hands the pixels to the LULinear path -- the folded run must then hold the LU map only (inside an
+    image chain the same leaf stands for permutation + LU)."""
+    g = load_golden("next_rows")
+    for key, channels in (("conv1x1", 3), ("conv1x1_c12", 12)):
+        r = g[key]
+        conv = T.OneByOneConvolution(channels, identity_init=False).eval()
+        conv.load_state_dict(r["sd"], strict=True)
+        y, lad = conv(r["x"])
+        assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= TOL, key
+        back, _ = conv.inverse(r["y"])
+        assert rel_err(back, r["x"]) <= 1e-4, key

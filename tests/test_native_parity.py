@@ -696,4 +696,4 @@ def test_image_flow_against_reference_golden(cuda_device):
     # batch split consistency: images are independent
     lp2 = torch.cat([flow.log_prob(x[:2]), flow.log_prob(x[2:])])
     assert rel_err(lp2.cpu(), lp.cpu()) <= 1e-6
-    assert flow.sample(3).shape == (3, 3 * 16 * 16)
+    assert flow.sample(3).shape == (3, 3, 16, 16)
