@@ -65,7 +65,32 @@ def warn_eager_cuda(t, module=None):
                   "the parameters) to run the sm_100a kernels.", RuntimeWarning, stacklevel=3)
 
 
+_DEFERRED = [None]
+
+
+class deferred_flags:
+    """`with deferred_flags(device) as d:` -- native calls inside the block share ONE device flag word and do not read it back
+    (no host synchronisation per call: a caller that streams many chunks through a flow keeps the GPU fed); the caller reads
+    `d.value()` once at the end and acts on it (raise_for_flag_value, or repeat with a smaller activation exponent)."""
+
+    def __init__(self, device):
+        self.flags = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def __enter__(self):
+        self.prev, _DEFERRED[0] = _DEFERRED[0], self
+        return self
+
+    def __exit__(self, *exc):
+        _DEFERRED[0] = self.prev
+
+    def value(self):
+        return int(self.flags.item())
+
+
 def new_flags(device):
+    d = _DEFERRED[0]
+    if d is not None and d.flags.device == torch.device(device):
+        return d.flags
     return torch.zeros(1, dtype=torch.int32, device=device)
 
 
@@ -201,7 +226,7 @@ def run_with_activation_rescale(fn):
     try:
         while True:
             out, lad, flags = fn()
-            if not config.check_domain:
+            if not config.check_domain or (_DEFERRED[0] is not None and flags is _DEFERRED[0].flags):
                 return out, lad
             v = int(flags.item())
             if (v & 4) and config.auto_activation_exp and config.activation_exp > -24:

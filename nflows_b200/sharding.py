@@ -54,10 +54,31 @@ def log_prob_sharded(flow, inputs, context=None, group=None, gather=True):
 def log_prob_streamed(flow, host_inputs, device, chunk_rows=1 << 16, out=None):
     """Flow.log_prob of a (pinned) HOST tensor: chunks are copied on a side stream while the previous chunk is being
     evaluated, so the host->device transfer hides behind the kernels.  Returns the [n_rows] result on `device`."""
+    from . import config
+    from . import kernels as K
     n = host_inputs.shape[0]
     result = out if out is not None else torch.empty(n, dtype=torch.float32, device=device)
     if n == 0:
         return result
+    # One flag read for the whole call instead of one per chunk (each read would drain the GPU while the host prepares the next
+    # chunk's launches); a range flag repeats the call with a smaller activation exponent, like a single Flow.log_prob does.
+    saved = config.activation_exp
+    try:
+        while True:
+            with K.deferred_flags(torch.device(device)) as deferred:
+                _stream_chunks(flow, host_inputs, device, chunk_rows, result)
+            v = deferred.value() if config.check_domain else 0
+            if (v & 4) and config.auto_activation_exp and config.activation_exp > -24:
+                config.activation_exp = max(-24, config.activation_exp - 5)
+                continue
+            K.raise_for_flag_value(v)
+            return result
+    finally:
+        config.activation_exp = saved
+
+
+def _stream_chunks(flow, host_inputs, device, chunk_rows, result):
+    n = host_inputs.shape[0]
     copy_stream = torch.cuda.Stream(device=device)
     compute = torch.cuda.current_stream(device)
     buffers, ready = [None, None], [None, None]
@@ -87,4 +108,3 @@ def log_prob_streamed(flow, host_inputs, device, chunk_rows=1 << 16, out=None):
         done = torch.cuda.Event()
         done.record(compute)
         ready[i] = done
-    return result
