@@ -83,25 +83,32 @@ def _stream_chunks(flow, host_inputs, device, chunk_rows, result):
     compute = torch.cuda.current_stream(device)
     buffers, ready = [None, None], [None, None]
 
-    def stage(i, lo):
-        hi = min(n, lo + chunk_rows)
+    # chunk boundaries: a short first chunk (its copy is the only one nothing hides) and a half one, then full chunks
+    bounds, lo = [], 0
+    for size in (max(4096, chunk_rows // 8), max(4096, chunk_rows // 2)):
+        if n - lo > chunk_rows:
+            bounds.append((lo, lo + size))
+            lo += size
+    while lo < n:
+        bounds.append((lo, min(n, lo + chunk_rows)))
+        lo = bounds[-1][1]
+
+    def stage(i, k):
+        lo, hi = bounds[k]
         with torch.cuda.stream(copy_stream):
             if buffers[i] is not None:
                 copy_stream.wait_event(ready[i])          # previous consumer of this buffer has finished
             buffers[i] = host_inputs[lo:hi].to(device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return hi, ev
+        return ev
 
-    starts = list(range(0, n, chunk_rows))
-    hi, ev = stage(0, starts[0])
-    pending = (0, starts[0], hi, ev)
-    for k in range(len(starts)):
-        i, lo, hi, ev = pending
-        if k + 1 < len(starts):
+    pending = (0, stage(0, 0))
+    for k, (lo, hi) in enumerate(bounds):
+        i, ev = pending
+        if k + 1 < len(bounds):
             j = (k + 1) & 1
-            nhi, nev = stage(j, starts[k + 1])
-            pending = (j, starts[k + 1], nhi, nev)
+            pending = (j, stage(j, k + 1))
         compute.wait_event(ev)
         buffers[i].record_stream(compute)
         result[lo:hi] = flow.log_prob(buffers[i])

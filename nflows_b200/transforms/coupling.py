@@ -199,6 +199,8 @@ class CouplingTransform(Transform):
         chain = net.dense_chain(context) if hasattr(net, "dense_chain") else None
         n_params = self.num_transform_features * self._transform_dim_multiplier()
         trunk_rows = D.whole_images(1 << 15)
+        if chain is None and net.training and any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in net.modules()):
+            trunk_rows = max(1, n)      # a batch-dependent conditioner must see the whole batch (statistics, running averages)
         use_tc = chain is not None and D.chain_uses_tc(chain, self.num_identity_features)
         final_rows = self._conditioner_rows(n_params)
         if use_tc and self._fused_final_ready(chain):
