@@ -112,6 +112,19 @@ int nfk_absmax(const float* x, int64_t ldx, int64_t n_rows, int32_t n_cols, floa
 int nfk_split_f16(const float* x, int64_t ldx, int32_t n_cols, int relu, int32_t scale_exp, void* hi, void* lo, int64_t ldo,
                   int64_t n_rows, int32_t* flags, void* stream);
 
+/* Affine / additive coupling with the LAST conditioner layer fused in (coupling.py:212-269 + the final nn.Linear of the
+ * conditioner, nn/nets/resnet.py:99): params = a W^T + bias is formed on the tensor cores (operands as for nfk_linear_f16x3)
+ * and consumed in the epilogue's registers -- y_j = x_j * s_j + t_j (inverse: (x_j - t_j) / s_j), lad_accum[n] += +-sum log s_j
+ * -- the [n_rows, mult*d_t] parameter tensor is never written.  The weight rows / bias entries must be INTERLEAVED when
+ * mult == 2: row 2j = shift of feature j, row 2j+1 = its unconstrained scale (the reference's BLOCKED order is rows j and
+ * d_t + j).  scale_activation as nfk_affine_coupling_rows.  Only the transformed columns of y are written (y may alias x).
+ * lad_accum is updated with atomicAdd (a row's columns are spread over several threads): the sum order is not fixed. */
+int nfk_affine_coupling_final_f16x3(const void* a_hi, const void* a_lo, int64_t lda, int32_t a_exp, const void* w_hi,
+                                    const void* w_lo, int64_t ldw, int32_t w_exp, const float* bias, int32_t hidden_features,
+                                    const float* x, int64_t ldx, const int32_t* t_cols, int32_t t_col0, int32_t d_t, int32_t mult,
+                                    int32_t scale_activation, int inverse, float* y, int64_t ldy, float* lad_accum, int64_t n_rows,
+                                    int32_t* flags, void* stream);
+
 /* Context gate + skip connection of a residual block (nn/nets/resnet.py:50-53: `F.glu(cat(temps, context_layer(context)))`
  * then `inputs + temps`):  v = skip + t * sigmoid(gate)  (skip may be NULL).  Writes v as fp32 (y, may be NULL) and / or as the
  * fp16 pair of pre(v) * 2^y_exp (pre = relu when split_relu) that the next dense layer multiplies. */

@@ -68,6 +68,8 @@ _SIGNATURES = {
     "nfk_squeeze_rows": (c_int, [_P, _P, c_int64, c_int32, c_int32, c_int32, c_int, _P]),
     "nfk_im2col3x3_f16": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
     "nfk_segment_sum": (c_int, [_P, _P, c_int64, c_int32, _P]),
+    "nfk_affine_coupling_final_f16x3": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P, c_int32, _P, c_int64, _P, c_int32,
+                                                c_int32, c_int32, c_int32, c_int, _P, c_int64, _P, c_int64, _P, _P]),
     "nfk_glu_skip_rows": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int, c_int64, c_int32,
                                   _P, _P]),
     "nfk_residual_trunk_f16x3_supported": (c_int, [c_int32, c_int32, c_int64, c_int64]),

@@ -71,6 +71,14 @@ struct Params {
     int mma_warps;           // 2: two MMA-issuing warps take alternate partial sums
     int drain;               // K-slabs accumulated in TMEM per partial sum (DRAIN_SLABS_LINEAR by default)
     int w_slot_bytes;        // bytes per W ring slot (hi part first, lo part at w_slot_bytes / 2)
+    // affine-coupling epilogue (nfk_affine_coupling_final_f16x3): the GEMM result is the conditioner's parameter row --
+    // interleaved (shift_j, raw scale_j) pairs when c_mult == 2, shift_j when 1 -- consumed in registers, never stored
+    const float* cx;         // coupling input [n_rows, ldcx]; NULL = plain dense layer
+    float* cy;               // coupling output [n_rows, ldcy] (transformed columns only; may alias cx)
+    const int32_t* c_cols;   // column of transformed feature j, or NULL: c_col0 + j
+    float* c_lad;            // running log|det| per row (atomicAdd of this thread's share), may be NULL
+    int64_t ldcx, ldcy;
+    int c_col0, c_dt, c_mult, c_act, c_inverse;
 };
 
 // Operand rings share LIN_RING_BYTES: LIN_W_STAGES weight slots of [W hi | W lo] sized for the launch's column tile (BN rows of
@@ -515,6 +523,42 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         stg_buf = 0;
                     }
                 }
+            } else if (p.cx) {
+                // ---- affine / additive coupling (coupling.py:212-269 of the reference) on the parameters held in registers:
+                // y_j = x_j * s_j + t_j (inverse: (x_j - t_j) / s_j), log|det| += +-sum_j log s_j
+                float lad = 0.0f;
+                if (row < p.n_rows) {
+#pragma unroll
+                    for (int c = 0; c < HALF; c += 2) {
+                        const int col = n0 + c;                            // even: tiles and halves start on even columns
+                        if (c + half * HALF >= p.BN || col >= p.N) continue;
+                        const float a0 = sum[c] * p.inv_acc_scale, a1 = sum[c + 1] * p.inv_acc_scale;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int j = p.c_mult == 2 ? (col >> 1) : col + e;
+                            if ((p.c_mult == 2 && e == 1) || j >= p.c_dt) continue;
+                            const int cf = p.c_cols ? __ldg(p.c_cols + j) : p.c_col0 + j;
+                            const float x = p.cx[row * p.ldcx + cf];
+                            const float shift = (p.c_mult == 2 || e == 0) ? a0 : a1;
+                            float out;
+                            if (p.c_mult == 2) {
+                                float scale;
+                                if (p.c_act == 0) {
+                                    scale = 1.0f / (1.0f + expf(-(a1 + 2.0f))) + 1e-3f;
+                                } else {
+                                    const float sp = a1 > 20.0f ? a1 : log1pf(expf(a1));
+                                    scale = fminf(fmaxf(sp + 1e-3f, 0.0f), 3.0f);
+                                }
+                                lad += logf(scale);
+                                out = p.c_inverse ? __fdiv_rn(__fsub_rn(x, shift), scale) : __fadd_rn(__fmul_rn(x, scale), shift);
+                            } else {
+                                out = p.c_inverse ? (x - shift) : (x + shift);
+                            }
+                            p.cy[row * p.ldcy + cf] = out;
+                        }
+                    }
+                    if (p.c_lad && p.c_mult == 2) atomicAdd(p.c_lad + row, p.c_inverse ? -lad : lad);
+                }
             } else if (row < p.n_rows) {
 #pragma unroll
                 for (int c = 0; c < HALF; c += 16) {
@@ -782,18 +826,53 @@ extern "C" int nfk_linear_f16x3_supported(int64_t lda, int64_t ldw, int32_t in_f
     return (in_features >= 8 && in_features % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0) ? 1 : 0;
 }
 
+namespace {
+struct CouplingEpilogue {        // set by nfk_affine_coupling_final_f16x3
+    const float* x; int64_t ldx; float* y; int64_t ldy; const int32_t* t_cols; int t_col0, d_t, mult, act, inverse; float* lad;
+};
+}  // namespace
+
+static int linear_f16x3_launch(const void* a_hi_, const void* a_lo_, int64_t lda, int32_t a_exp, const void* w_hi_,
+                               const void* w_lo_, int64_t ldw, int32_t w_exp, const float* bias, const float* R, int64_t ldr,
+                               float* Y, int64_t ldy, void* y_hi_, void* y_lo_, int64_t lds, int32_t y_exp, int32_t split_cols,
+                               int32_t y_first_col, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
+                               int32_t out_features, int32_t* flags, void* stream, const CouplingEpilogue* ce);
+
 extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t lda, int32_t a_exp, const void* w_hi_,
                                 const void* w_lo_, int64_t ldw, int32_t w_exp, const float* bias, const float* R, int64_t ldr,
                                 float* Y, int64_t ldy, void* y_hi_, void* y_lo_, int64_t lds, int32_t y_exp, int32_t split_cols,
                                 int32_t y_first_col, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
                                 int32_t out_features, int32_t* flags, void* stream) {
+    NFK_REQUIRE(Y || (y_hi_ && y_lo_), "no output requested");
+    return linear_f16x3_launch(a_hi_, a_lo_, lda, a_exp, w_hi_, w_lo_, ldw, w_exp, bias, R, ldr, Y, ldy, y_hi_, y_lo_, lds, y_exp,
+                               split_cols, y_first_col, relu_out, split_relu, n_rows, in_features, out_features, flags, stream, nullptr);
+}
+
+extern "C" int nfk_affine_coupling_final_f16x3(const void* a_hi, const void* a_lo, int64_t lda, int32_t a_exp, const void* w_hi,
+                                               const void* w_lo, int64_t ldw, int32_t w_exp, const float* bias, int32_t hidden_features,
+                                               const float* x, int64_t ldx, const int32_t* t_cols, int32_t t_col0, int32_t d_t,
+                                               int32_t mult, int32_t scale_activation, int inverse, float* y, int64_t ldy,
+                                               float* lad_accum, int64_t n_rows, int32_t* flags, void* stream) {
+    NFK_REQUIRE(d_t >= 1 && (mult == 1 || mult == 2) && (scale_activation == 0 || scale_activation == 1), "bad coupling description");
+    if (n_rows == 0) return NFK_OK;
+    NFK_REQUIRE(x && y && (t_cols || t_col0 >= 0), "NULL pointer");
+    CouplingEpilogue ce{x, ldx, y, ldy, t_cols, t_col0, d_t, mult, scale_activation, inverse, lad_accum};
+    return linear_f16x3_launch(a_hi, a_lo, lda, a_exp, w_hi, w_lo, ldw, w_exp, bias, nullptr, 0, nullptr, 0, nullptr, nullptr, 0, 0, 0, 0,
+                               0, 0, n_rows, hidden_features, mult * d_t, flags, stream, &ce);
+}
+
+static int linear_f16x3_launch(const void* a_hi_, const void* a_lo_, int64_t lda, int32_t a_exp, const void* w_hi_,
+                               const void* w_lo_, int64_t ldw, int32_t w_exp, const float* bias, const float* R, int64_t ldr,
+                               float* Y, int64_t ldy, void* y_hi_, void* y_lo_, int64_t lds, int32_t y_exp, int32_t split_cols,
+                               int32_t y_first_col, int relu_out, int split_relu, int64_t n_rows, int32_t in_features,
+                               int32_t out_features, int32_t* flags, void* stream, const CouplingEpilogue* ce) {
     const __half* a_hi = (const __half*)a_hi_; const __half* a_lo = (const __half*)a_lo_;
     const __half* w_hi = (const __half*)w_hi_; const __half* w_lo = (const __half*)w_lo_;
     __half* y_hi = (__half*)y_hi_; __half* y_lo = (__half*)y_lo_;
     NFK_REQUIRE(n_rows >= 0 && in_features >= 1 && out_features >= 1, "bad sizes");
     if (n_rows == 0) return NFK_OK;
     NFK_REQUIRE(a_hi && a_lo && w_hi && w_lo, "NULL operand pointer");
-    NFK_REQUIRE(Y || (y_hi && y_lo), "no output requested");
+    NFK_REQUIRE(ce || Y || (y_hi && y_lo), "no output requested");
     NFK_REQUIRE((y_hi == nullptr) == (y_lo == nullptr), "y_hi and y_lo must be given together");
     NFK_REQUIRE(nfk_linear_f16x3_supported(lda, ldw, in_features), "f16x3 path needs in_features, lda, ldw multiples of 8");
     NFK_REQUIRE(aligned16(a_hi) && aligned16(a_lo) && aligned16(w_hi) && aligned16(w_lo), "operands must be 16-byte aligned");
@@ -807,6 +886,12 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
     p.relu_out = relu_out; p.split_relu = split_relu;
     p.y_first_col = y_first_col > 0 ? y_first_col : 0;
+    p.cx = nullptr; p.cy = nullptr; p.c_cols = nullptr; p.c_lad = nullptr; p.ldcx = p.ldcy = 0;
+    p.c_col0 = p.c_dt = p.c_mult = p.c_act = p.c_inverse = 0;
+    if (ce) {
+        p.cx = ce->x; p.cy = ce->y; p.c_cols = ce->t_cols; p.c_lad = ce->lad; p.ldcx = ce->ldx; p.ldcy = ce->ldy;
+        p.c_col0 = ce->t_col0; p.c_dt = ce->d_t; p.c_mult = ce->mult; p.c_act = ce->act; p.c_inverse = ce->inverse;
+    }
     {
         static int mma_pref = 0, drain_pref = 0;
         if (!mma_pref) {
@@ -849,7 +934,7 @@ extern "C" int nfk_linear_f16x3(const void* a_hi_, const void* a_lo_, int64_t ld
     if ((rc = tc::make_map(&mw_lo, w_lo, out_features, in_features, ldw, bn / CL))) return rc;
     // staged TMA stores need 16-byte aligned bases and row pitches for every requested output
     CUtensorMap my = mw_hi, myh = mw_hi, myl = mw_hi, myt = mw_hi, myht = mw_hi, mylt = mw_hi;   // placeholders (never dereferenced)
-    p.tma_store = (!Y || (aligned16(Y) && ldy % 4 == 0)) && (!y_hi || (aligned16(y_hi) && aligned16(y_lo) && lds % 8 == 0)) ? 1 : 0;
+    p.tma_store = (!ce && (!Y || (aligned16(Y) && ldy % 4 == 0)) && (!y_hi || (aligned16(y_hi) && aligned16(y_lo) && lds % 8 == 0))) ? 1 : 0;
     if (p.tma_store) {
         const int64_t pn = p.split_n < out_features ? p.split_n : out_features;
         if (Y && (rc = tc::make_store_map(&my, Y, false, n_rows, out_features, ldy))) return rc;

@@ -332,6 +332,15 @@ def _run_trunk_block(chain, x, id_cols, use_tc, last_out, x_pair, flags):
             raise ValueError("a pre-split input cannot feed a layer that applies relu to its input")
         state = ChainState(pair=x_pair)
         skip_src = None
+        from . import config
+        if (config.coupling_step_kernel and type(chain) is list and len(body) >= 1 and plan_step_kernel(chain) is not None
+                and K.rq_coupling_step_supported(8, "linear", body[0][0].shape[0], x_pair.shape[1], len(body) - 1)):
+            # the whole trunk in ONE launch: the coupling-step kernel stopped after its last trunk layer (the activation pair
+            # stays in shared memory between the layers; only the last layer's pair is written)
+            out = last_out if last_out is not None else K.Pair16.empty(x_pair.shape[0], body[0][0].shape[0], act_exp(), x_pair.hi.device)
+            with K.timed("trunk_step", x_pair.shape[0]):
+                K.rq_coupling_step(step_plan(chain), x_pair, h_pair=out, flags=flags)
+            return ChainState(pair=out)
         trunk_flags = plan_trunk_kernel(chain) if trunk_kernel_enabled() else None
         if trunk_flags is not None:
             # first layer as a GEMM of its own (its K differs), everything up to the last layer in ONE persistent kernel
@@ -430,6 +439,27 @@ def affine_map(x, weight, bias, x_pair=None, pair_cols=0, flags=None, y_first_co
 
 
 _PACK_CACHE = {}
+
+
+def pack_final_affine(weight, bias, d_t, mult):
+    """Operands of nfk_affine_coupling_final_f16x3: the last conditioner layer with its rows INTERLEAVED (shift_j, raw scale_j)
+    instead of the reference's blocked [shifts | scales] (coupling.py:229-232), as a Pair16, plus the bias in the same order.
+    Cached until weight or bias is modified."""
+    w, b = weight.detach(), bias.detach()
+    key = (id(weight), "affine")
+    sig = (w.data_ptr(), w._version, b.data_ptr(), b._version, str(w.device), d_t, mult, cache_epoch())
+    hit = _PACK_CACHE.get(key)
+    if hit is None or hit[0] != sig:
+        if mult == 2:
+            wi = torch.stack([w[:d_t], w[d_t:]], dim=1).reshape(2 * d_t, w.shape[1]).contiguous()
+            bi = torch.stack([b[:d_t], b[d_t:]], dim=1).reshape(-1).contiguous()
+        else:
+            wi, bi = w.contiguous(), b.contiguous()
+        hit = (sig, K.split_f16(wi, K.weight_exp(wi)), bi.float(), weight)
+        _PACK_CACHE[key] = hit
+        if len(_PACK_CACHE) > 1024:
+            _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
+    return hit[1], hit[2]
 
 
 def pack_final_spline(weight, bias, d_t, m, mp):

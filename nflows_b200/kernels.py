@@ -327,6 +327,22 @@ def glu_skip(t, gate, skip=None, want_y=True, want_split=False, split_relu=False
     return y, pair
 
 
+def affine_coupling_final(a, w, bias, x, t_cols, mult, scale_activation, inverse, y, lad_accum, flags=None):
+    """Last conditioner layer + affine / additive coupling in one tcgen05 kernel (include/nfk.h:
+    nfk_affine_coupling_final_f16x3).  a: Pair16 of the trunk output; w, bias: dense.pack_final_affine (interleaved rows);
+    t_cols: int32 index tensor of the transformed columns or (first_column, count); writes the transformed columns of y."""
+    if isinstance(t_cols, tuple):
+        cols_ptr, col0, d_t = 0, int(t_cols[0]), int(t_cols[1])
+    else:
+        cols_ptr, col0, d_t = t_cols.data_ptr(), -1, t_cols.numel()
+    with timed("affine_coupling_final", x.shape[0]):
+        N.check(N.lib().nfk_affine_coupling_final_f16x3(
+            a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, w.hi.data_ptr(), w.lo.data_ptr(), w.hi.stride(0), w.exp,
+            bias.data_ptr(), a.shape[1], x.data_ptr(), x.stride(0), cols_ptr, col0, d_t, int(mult), int(scale_activation), int(inverse),
+            y.data_ptr(), y.stride(0), N.ptr(lad_accum), x.shape[0], N.ptr(flags), N.stream()))
+    return y
+
+
 # ---- image path: pixel rows (include/nfk.h, "image path") ----------------------------------------------------------------
 def nchw_to_rows(x):
     """[B, C, H, W] fp32 -> pixel rows [B*H*W, C]."""

@@ -138,7 +138,8 @@ class CouplingTransform(Transform):
         pair = carry["pair"] if carry is not None else None
         # the next leaf is a folded affine run: it multiplies the fp16 pair of this output, never the fp32 values, so the
         # fused kernel writes only the pair of the transformed block (x's transformed block is then stale and unread)
-        pair_only = bool(carry is not None and carry.get("pair_only") and config.fused_pair_only and d_id % 8 == 0)
+        pair_only = bool(carry is not None and carry.get("pair_only") and config.fused_pair_only and d_id % 8 == 0
+                         and self._fused_pair_output)
         if pair is None:
             pair = K.Pair16.empty(n, self.features, D.act_exp(), x.device)
             K.split_f16(x[:, :d_id], pair.exp, out=pair.cols(0, d_id), flags=flags)
@@ -251,6 +252,8 @@ class CouplingTransform(Transform):
     def _native_epilogue(self, x, params, t_cols, id_cols, out, lad, flags, inverse):
         raise NotImplementedError()
 
+    _fused_pair_output = True      # the fused final kernel can write the fp16 pair of its outputs instead of fp32
+
     def _fused_final_ready(self, chain):
         return False
 
@@ -312,6 +315,22 @@ class AffineCouplingTransform(CouplingTransform):
     def _native_epilogue(self, x, params, t_cols, id_cols, out, lad, flags, inverse):
         K.affine_coupling_rows(x, params, self._transform_dim_multiplier(), self._activation_code() or 0, inverse, t_cols,
                                id_cols, lad, out=out)
+
+    # the last conditioner layer fused with the coupling (nfk_affine_coupling_final_f16x3): the [B, 2*d_t] parameter tensor of
+    # coupling.py:229-232 is never written
+    _fused_pair_output = False
+
+    def _fused_final_ready(self, chain):
+        weight, bias, relu_in, relu_out, residual = chain[-1]
+        hidden = weight.shape[1]
+        return (config.fuse_coupling and bias is not None and not relu_out and residual is None and self._activation_code() is not None
+                and K.f16x3_supported(hidden, hidden, hidden))
+
+    def _fused_final(self, chain, state, x, t_cols, out, lad, flags, inverse, y_pair=None):
+        weight, bias = chain[-1][0], chain[-1][1]
+        mult = self._transform_dim_multiplier()
+        w_pair, bias_i = D.pack_final_affine(weight, bias, self.num_transform_features, mult)
+        K.affine_coupling_final(state.pair, w_pair, bias_i, x, t_cols, mult, self._activation_code() or 0, inverse, out, lad, flags)
 
 
 class AdditiveCouplingTransform(AffineCouplingTransform):

@@ -407,8 +407,54 @@ def image_rows():
     save("image_rows", rec)
 
 
+def affine_rows():
+    """Round 2 (row ns2): affine / additive couplings at sizes the tensor-core dense path takes -- D = 48 (alternating mask: 24
+    identity columns: packed path) and D = 20 (8 identity / 12 transformed columns: gathered path), hidden 64, both scale activations -- and a
+    small RealNVP-style flow of them behind ActNorm + LU layers (column layouts)."""
+    rec = {}
+    with torch.no_grad():
+        torch.manual_seed(40)
+        f = lambda i, o: ResidualNet(i, o, hidden_features=64, num_blocks=2)
+        for name, d, mask_fn, kw in (
+                ("default48", 48, torchutils.create_alternating_binary_mask, {}),
+                ("general48", 48, torchutils.create_alternating_binary_mask,
+                 dict(scale_activation=T.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION)),
+                ("default20", 20, lambda d: torch.tensor([0] * 8 + [1] * 12), {})):
+            t = T.AffineCouplingTransform(mask_fn(d), f, **kw).eval()
+            for n_, p in t.named_parameters():
+                if "final_layer" in n_ or "blocks.1.linear_layers.1" in n_:
+                    p.mul_(4.0)
+            x = torch.randn(700, d) * 1.5
+            y, lad = t(x)
+            xi, li = t.inverse(x)
+            y64, lad64 = t.double()(x.double())
+            t.float()
+            rec[name] = dict(sd=t.state_dict(), x=x, y=y, lad=lad, xinv=xi, ladinv=li, y_fp64=y64, lad_fp64=lad64)
+        ta = T.AdditiveCouplingTransform(torchutils.create_alternating_binary_mask(48), f).eval()
+        for n_, p in ta.named_parameters():
+            if "final_layer" in n_:
+                p.mul_(4.0)
+        x = torch.randn(700, 48)
+        y, lad = ta(x)
+        rec["additive48"] = dict(sd=ta.state_dict(), x=x, y=y, lad=lad, xinv=ta.inverse(x)[0])
+        steps = []
+        for i in range(3):
+            steps += [T.ActNorm(48), T.CompositeTransform([T.RandomPermutation(48), T.LULinear(48, identity_init=True)]),
+                      T.AffineCouplingTransform(torchutils.create_alternating_binary_mask(48, even=(i % 2 == 0)), f)]
+        flow = Flow(T.CompositeTransform(steps), StandardNormal([48])).eval()
+        perturb(flow)
+        x = torch.randn(700, 48)
+        lp = flow.log_prob(x)
+        lp64 = flow.double().log_prob(x.double())
+        flow.float()
+        rec["flow48"] = dict(sd=flow.state_dict(), x=x, log_prob=lp, log_prob_fp64=lp64, z=flow.transform_to_noise(x))
+    save("affine_rows", rec)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "image_rows":
+    if len(sys.argv) > 1 and sys.argv[1] == "affine_rows":
+        affine_rows()
+    elif len(sys.argv) > 1 and sys.argv[1] == "image_rows":
         image_rows()
     elif len(sys.argv) > 1 and sys.argv[1] == "next_rows":
         next_rows()
@@ -419,3 +465,4 @@ if __name__ == "__main__":
         next_rows()
         context_rows()
         image_rows()
+        affine_rows()

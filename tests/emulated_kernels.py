@@ -206,6 +206,37 @@ def install(monkeypatch):
         y[:, t] = yt
         return y
 
+    def affine_coupling_rows(x, params, mult, scale_activation, inverse, t_cols, id_cols, lad_accum, out=None):
+        count("affine_coupling_rows")
+        y = torch.empty_like(x) if out is None else out
+        t, d_t = t_cols.long(), t_cols.numel()
+        y[:, id_cols.long()] = x[:, id_cols.long()]
+        shift = params[:, :d_t]
+        if mult == 2:
+            raw = params[:, d_t:]
+            scale = torch.sigmoid(raw + 2) + 1e-3 if scale_activation == 0 else (F.softplus(raw) + 1e-3).clamp(0, 3)
+            y[:, t] = (x[:, t] - shift) / scale if inverse else x[:, t] * scale + shift
+            lad_accum += -torch.log(scale).sum(dim=1) if inverse else torch.log(scale).sum(dim=1)
+        else:
+            y[:, t] = x[:, t] - shift if inverse else x[:, t] + shift
+        return y
+
+    def affine_coupling_final(a, w, bias, x, t_cols, mult, scale_activation, inverse, y, lad_accum, flags=None):
+        count("affine_coupling_final")
+        t = _cols(t_cols, x.shape[1])
+        params = (_value(a) @ _value(w).t() + bias.double()).float()
+        xt = x[:, t]
+        if mult == 2:
+            shift, raw = params[:, 0::2], params[:, 1::2]
+            scale = torch.sigmoid(raw + 2) + 1e-3 if scale_activation == 0 else (F.softplus(raw) + 1e-3).clamp(0, 3)
+            lad = torch.log(scale).sum(dim=1)
+            y[:, t] = (xt - shift) / scale if inverse else xt * scale + shift
+            if lad_accum is not None:
+                lad_accum += -lad if inverse else lad
+        else:
+            y[:, t] = xt - params if inverse else xt + params
+        return y
+
     # the functional spline API keeps its torch formulation (it is what the stand-ins of the spline kernels call)
     monkeypatch.setattr(splines.rational_quadratic, "_use_native", lambda inputs, *params: False)
     for name, fn in dict(
@@ -218,7 +249,7 @@ def install(monkeypatch):
             nchw_to_rows=nchw_to_rows, rows_to_nchw=rows_to_nchw, squeeze_rows=squeeze_rows, im2col3x3=im2col3x3,
             segment_sum_=segment_sum_, f16x3_supported=f16x3_supported, linear_f16x3=linear_f16x3,
             rq_coupling_final_supported=rq_coupling_final_supported, rq_coupling_final_padded_params=rq_coupling_final_padded_params,
-            rq_coupling_final=rq_coupling_final, rq_coupling_step_supported=lambda *a: False,
+            rq_coupling_final=rq_coupling_final, affine_coupling_final=affine_coupling_final, affine_coupling_rows=affine_coupling_rows, rq_coupling_step_supported=lambda *a: False,
             residual_trunk_supported=lambda *a: False).items():
         monkeypatch.setattr(K, name, fn)
     return calls

@@ -102,3 +102,50 @@ def test_standalone_one_by_one_convolution_through_the_native_chain(emu):
         assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= TOL, key
         back, _ = conv.inverse(r["y"])
         assert rel_err(back, r["x"]) <= 1e-4, key
+
+
+def _affine_cases(g):
+    from nflows_b200.nn.nets import ResidualNet
+    from nflows_b200.utils import torchutils
+    f = lambda i, o: ResidualNet(i, o, hidden_features=64, num_blocks=2)
+    alt, mid = torchutils.create_alternating_binary_mask, torchutils.create_mid_split_binary_mask
+    yield "default48", T.AffineCouplingTransform(alt(48), f)
+    yield "general48", T.AffineCouplingTransform(alt(48), f, scale_activation=T.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION)
+    yield "default20", T.AffineCouplingTransform(torch.tensor([0] * 8 + [1] * 12), f)
+    yield "additive48", T.AdditiveCouplingTransform(alt(48), f)
+
+
+@torch.no_grad()
+def test_affine_couplings_with_the_fused_final_layer(emu):
+    """Row ns2: affine / additive couplings whose last conditioner layer is fused with the coupling (interleaved weight rows,
+    packed and gathered column paths) against the reference golden affine_rows.pt."""
+    g = load_golden("affine_rows")
+    for key, t in _affine_cases(g):
+        r = g[key]
+        t = t.eval()
+        t.load_state_dict(r["sd"], strict=True)
+        y, lad = t(r["x"])
+        assert rel_err(y, r["y"]) <= TOL and rel_err(lad, r["lad"]) <= 3e-5, key
+        xi, _ = t.inverse(r["x"])
+        assert rel_err(xi, r["xinv"]) <= 1e-4, key
+    assert emu.get("affine_coupling_final", 0) == 8 and emu.get("rqs_rows", 0) == 0
+
+
+@torch.no_grad()
+def test_affine_flow_behind_folded_affine_runs(emu):
+    """ActNorm + LU runs in front of affine couplings: the coupling asks for the identity-first column layout, the fold emits it."""
+    from nflows_b200.distributions.normal import StandardNormal
+    from nflows_b200.flows import Flow
+    from nflows_b200.nn.nets import ResidualNet
+    from nflows_b200.utils import torchutils
+    r = load_golden("affine_rows")["flow48"]
+    f = lambda i, o: ResidualNet(i, o, hidden_features=64, num_blocks=2)
+    steps = []
+    for i in range(3):
+        steps += [T.ActNorm(48), T.CompositeTransform([T.RandomPermutation(48), T.LULinear(48, identity_init=True)]),
+                  T.AffineCouplingTransform(torchutils.create_alternating_binary_mask(48, even=(i % 2 == 0)), f)]
+    flow = Flow(T.CompositeTransform(steps), StandardNormal([48])).eval()
+    flow.load_state_dict(r["sd"], strict=True)
+    lp = flow.log_prob(r["x"])
+    assert emu.get("affine_coupling_final", 0) == 3 and emu.get("gather_cols", 0) <= 2
+    assert rel_err(lp, r["log_prob_fp64"]) <= max(TOL, 3 * rel_err(r["log_prob"], r["log_prob_fp64"]))

@@ -697,3 +697,54 @@ def test_image_flow_against_reference_golden(cuda_device):
     lp2 = torch.cat([flow.log_prob(x[:2]), flow.log_prob(x[2:])])
     assert rel_err(lp2.cpu(), lp.cpu()) <= 1e-6
     assert flow.sample(3).shape == (3, 3, 16, 16)
+
+
+@torch.no_grad()
+def test_affine_couplings_fused_final_layer_against_reference_golden(cuda_device):
+    """Row ns2 (north_star: AffineCouplingTransform gets the same fused treatment): the last conditioner layer and the affine /
+    additive coupling run as ONE tcgen05 kernel (nfk_affine_coupling_final_f16x3), the trunk before it as one launch of the
+    coupling-step kernel stopped after its last trunk layer; reference outputs in tests/golden/affine_rows.pt."""
+    from nflows_b200.distributions.normal import StandardNormal
+    from nflows_b200.flows import Flow
+    g = load_golden("affine_rows")
+    f = lambda i, o: ResidualNet(i, o, hidden_features=64, num_blocks=2)
+    alt = torchutils.create_alternating_binary_mask
+    cases = [("default48", T.AffineCouplingTransform(alt(48), f)),
+             ("general48", T.AffineCouplingTransform(alt(48), f, scale_activation=T.AffineCouplingTransform.GENERAL_SCALE_ACTIVATION)),
+             ("default20", T.AffineCouplingTransform(torch.tensor([0] * 8 + [1] * 12), f)),
+             ("additive48", T.AdditiveCouplingTransform(alt(48), f))]
+    for key, t in cases:
+        r = g[key]
+        t.load_state_dict(r["sd"], strict=True)
+        t = to_dev(t, cuda_device)
+        x = r["x"].to(cuda_device)
+        K.TIMELINE = []
+        try:
+            with native_launches():
+                y, lad = t(x)
+            tags = {e[0] for e in K.TIMELINE}
+        finally:
+            K.TIMELINE = None
+        assert "affine_coupling_final" in tags and "trunk_step" in tags, (key, tags)
+        idf = t.identity_features.cpu()
+        assert torch.equal(y.cpu()[:, idf], r["x"][:, idf]), key
+        if "y_fp64" in r:
+            assert rel_err(y.cpu(), r["y_fp64"]) <= max(TOL, 3 * rel_err(r["y"], r["y_fp64"])), key
+            assert rel_err(lad.cpu(), r["lad_fp64"]) <= max(TOL, 3 * rel_err(r["lad"], r["lad_fp64"])), key
+        else:
+            assert rel_err(y.cpu(), r["y"]) <= TOL and torch.equal(lad.cpu(), torch.zeros(x.shape[0])), key
+        xi, li = t.inverse(x)
+        assert rel_err(xi.cpu(), r["xinv"]) <= 1e-4, key
+        if "ladinv" in r:
+            assert rel_err(li.cpu(), r["ladinv"]) <= 3e-5, key
+    r = g["flow48"]
+    steps = []
+    for i in range(3):
+        steps += [T.ActNorm(48), T.CompositeTransform([T.RandomPermutation(48), T.LULinear(48, identity_init=True)]),
+                  T.AffineCouplingTransform(alt(48, even=(i % 2 == 0)), f)]
+    flow = Flow(T.CompositeTransform(steps), StandardNormal([48])).eval()
+    flow.load_state_dict(r["sd"], strict=True)
+    flow = flow.to(cuda_device)
+    lp = flow.log_prob(r["x"].to(cuda_device))
+    assert rel_err(lp.cpu(), r["log_prob_fp64"]) <= max(TOL, 3 * rel_err(r["log_prob"], r["log_prob_fp64"]))
+    assert rel_err(flow.transform_to_noise(r["x"].to(cuda_device)).cpu(), r["z"]) <= 5e-5
