@@ -613,7 +613,9 @@ def test_autoregressive_rq_transform_cfg4(cuda_device):
         y2, lad2 = ar(x)
     finally:
         config.fuse_coupling = True
-    assert rel_err(y2, y) <= 2e-5
+    # (two of our own routes: each is held to the fp64 sandwich; against each other only loosely -- sharp bins amplify the
+    # last-bit differences of the two dense-layer schedules)
+    assert rel_err(y2.cpu(), g["y_fp64"]) <= max(TOL, 3 * rel_err(g["y"], g["y_fp64"])) and rel_err(y2, y) <= 5e-5
 
 
 @torch.no_grad()
