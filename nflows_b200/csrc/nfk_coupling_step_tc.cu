@@ -507,11 +507,18 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     if ((lf & SL_ADD_SKIP) && n0 + c < p.H) r4 = skip[(size_t)((n0 + c) >> 2) * 128];
                     sum[c] = r4.x; sum[c + 1] = r4.y; sum[c + 2] = r4.z; sum[c + 3] = r4.w;
                 }
+                {   // bias: ONE coalesced float4 load per thread (lane l: columns 4l..4l+3 of this thread's CT columns), broadcast by
+                    // shuffles -- a broadcast load per float4, each followed by its adds, serialises CT/4 L2 latencies per layer
+                    // (measured in the dense-layer kernel, r2: 8 600 cycles per tile)
+                    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (4 * lane < CT && n0 + 4 * lane < p.H)
+                        mine = __ldg(reinterpret_cast<const float4*>(p.bias_trunk + l * p.H + n0 + 4 * lane));
 #pragma unroll
-                for (int c = 0; c < CT; c += 4) {
-                    if (n0 + c < p.H) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias_trunk + l * p.H + n0 + c));
-                        sum[c] += b4.x; sum[c + 1] += b4.y; sum[c + 2] += b4.z; sum[c + 3] += b4.w;
+                    for (int c = 0; c < CT; c += 4) {
+                        sum[c] += __shfl_sync(0xffffffffu, mine.x, c >> 2);
+                        sum[c + 1] += __shfl_sync(0xffffffffu, mine.y, c >> 2);
+                        sum[c + 2] += __shfl_sync(0xffffffffu, mine.z, c >> 2);
+                        sum[c + 3] += __shfl_sync(0xffffffffu, mine.w, c >> 2);
                     }
                 }
                 const float as = p.acc_scale[l], ias = p.inv_acc_scale[l];

@@ -79,6 +79,7 @@ struct Params {
     float* c_lad;            // running log|det| per row (atomicAdd of this thread's share), may be NULL
     int64_t ldcx, ldcy;
     int c_col0, c_dt, c_mult, c_act, c_inverse;
+    long long* prof;         // NFK_LINEAR_PROF=<device address>: per-CTA cycle counters [8] (scripts/linear_prof.py), else NULL
 };
 
 // Operand rings share LIN_RING_BYTES: LIN_W_STAGES weight slots of [W hi | W lo] sized for the launch's column tile (BN rows of
@@ -252,6 +253,8 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             int sw_i = 0; uint32_t pw = 0;
             uint32_t gc = 0;                                              // partial sums so far: buffer gc & 1, use gc >> 1 of it
             int tm, tn;
+            long long t_tempty = 0, t_full = 0;
+            const long long t_begin = p.prof ? clock64() : 0;
             for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
                 for (int g = 0; g < num_groups; ++g, ++gc) {
                     const int slabs = min(p.drain, num_k - g * p.drain);
@@ -264,12 +267,16 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     }
                     const int acc = gc & 1u;
                     const uint32_t acc_phase = (gc >> 1) & 1u;
+                    long long t0 = p.prof ? clock64() : 0;
                     if (PAIR) mbar_wait_cluster(bar_tempty + 8 * acc, acc_phase ^ 1);   // both CTAs' epilogues have drained it
                     else mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);  // epilogue has drained this partial accumulator
+                    if (p.prof) t_tempty += clock64() - t0;
                     const uint32_t d_tmem = tmem_base + acc * BN_MAX;
                     for (int j = 0; j < slabs; ++j) {
+                        if (p.prof) t0 = clock64();
                         mbar_wait(bar_afull + 8 * sa_i, pa);               // TMA bytes have landed
                         mbar_wait(bar_wfull + 8 * sw_i, pw);
+                        if (p.prof) t_full += clock64() - t0;
                         tc_fence_after();
                         const uint32_t sa = smem_base + sa_i * LIN_A_STAGE_BYTES;
                         const uint32_t sw = ring_w + sw_i * LIN_W_STAGE_BYTES;
@@ -304,6 +311,10 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     }
                 }
             }
+            if (p.prof && warp == 1) {
+                long long* o = p.prof + (size_t)blockIdx.x * 16;
+                o[0] = clock64() - t_begin; o[1] = t_tempty; o[2] = t_full;
+            }
         }
     }
     } else {
@@ -322,7 +333,30 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const uint32_t stg_u32 = smem_base + LIN_STG_OFF + (warp - 4) * 2 * LIN_STG_BYTES;
         int stg_buf = 0;
         int tm, tn;
+        long long t_tfull = 0, t_out = 0, t_pro = 0, t_drain = 0, t_bias = 0, t_wait = 0, t_y = 0, t_pair = 0;
+        const long long e_begin = p.prof ? clock64() : 0;
+        // this lane's float4 of the bias of tile `it` (zeros past the tile / the matrix, or without a bias)
+        auto bias_of = [&](int it) -> float4 {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            int bm, bn;
+            if (p.bias && tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, bm, bn)) {
+                const int c = 4 * lane, col = bn * p.BN + half * HALF + c;
+                if (c + half * HALF < p.BN) {
+                    if (vec_b && col + 3 < p.N) {
+                        b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    } else {
+                        if (col < p.N) b.x = __ldg(p.bias + col);
+                        if (col + 1 < p.N) b.y = __ldg(p.bias + col + 1);
+                        if (col + 2 < p.N) b.z = __ldg(p.bias + col + 2);
+                        if (col + 3 < p.N) b.w = __ldg(p.bias + col + 3);
+                    }
+                }
+            }
+            return b;
+        };
+        float4 bias_cur = bias_of(0);
         for (int it = 0; tile_of<CL>(it, p.n_inner, p.num_m_tiles, p.num_n_tiles, cta_rank, tm, tn); ++it) {
+            long long e0 = p.prof ? clock64() : 0;
             const int64_t row = (int64_t)tm * BM + q * 32 + lane;
             const int n0 = tn * p.BN + half * HALF;
             // The running sums start from bias (+ residual when no relu sits between them): the loads are issued here, at the
@@ -343,48 +377,55 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
             }
             float sum[HALF];
-            // pass 1: every residual load is issued before anything depends on one (in-order issue: a dependent add between
-            // two loads would serialise the DRAM latencies)
-#pragma unroll
-            for (int c = 0; c < HALF; c += 4) {
-                const int col = n0 + c;
-                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (fold_residual && row < p.n_rows && c + half * HALF < p.BN) {
-                    if (vec_r && col + 3 < p.N) {
-                        r4 = __ldcs(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
-                    } else {
-                        const float* rp = p.residual + row * p.ldr + col;
-                        if (col < p.N) r4.x = rp[0];
-                        if (col + 1 < p.N) r4.y = rp[1];
-                        if (col + 2 < p.N) r4.z = rp[2];
-                        if (col + 3 < p.N) r4.w = rp[3];
-                    }
-                }
-                sum[c] = r4.x; sum[c + 1] = r4.y; sum[c + 2] = r4.z; sum[c + 3] = r4.w;
-            }
-            // pass 2: bias (L1-resident broadcast loads)
-            if (p.bias) {
+            const long long b0 = p.prof ? clock64() : 0;
+            // The running sums live in the accumulators' power-of-two scaled domain (exact) and start from the bias: ONE coalesced
+            // float4 per thread (lane l: columns 4l..4l+3 of this warp's column half; fetched during the PREVIOUS tile, see
+            // bias_of) broadcast by shuffles.  The first form -- 32 broadcast float4 loads, each followed by its adds -- serialised
+            // 32 L2 latencies per tile: 8 600 of a tile's 28 000 cycles, the MMA thread waiting for drained accumulators meanwhile
+            // (r2 cycle counters, scripts/linear_prof.py; L1 keeps little beside 227 KB of shared memory).
+            const float4 mine = make_float4(bias_cur.x * p.acc_scale, bias_cur.y * p.acc_scale, bias_cur.z * p.acc_scale,
+                                            bias_cur.w * p.acc_scale);
+            if (fold_residual) {
+                // residual rows straight into the sums, every load issued before anything depends on one (a dependent add between
+                // two loads would serialise the DRAM latencies), then scaled and joined with the bias
 #pragma unroll
                 for (int c = 0; c < HALF; c += 4) {
                     const int col = n0 + c;
-                    if (c + half * HALF < p.BN) {
-                        if (vec_b && col + 3 < p.N) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                            sum[c] += b4.x; sum[c + 1] += b4.y; sum[c + 2] += b4.z; sum[c + 3] += b4.w;
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < p.n_rows && c + half * HALF < p.BN) {
+                        if (vec_r && col + 3 < p.N) {
+                            r4 = __ldcs(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col));
                         } else {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (col + j < p.N) sum[c + j] += __ldg(p.bias + col + j);
+                            const float* rp = p.residual + row * p.ldr + col;
+                            if (col < p.N) r4.x = rp[0];
+                            if (col + 1 < p.N) r4.y = rp[1];
+                            if (col + 2 < p.N) r4.z = rp[2];
+                            if (col + 3 < p.N) r4.w = rp[3];
                         }
                     }
+                    sum[c] = r4.x; sum[c + 1] = r4.y; sum[c + 2] = r4.z; sum[c + 3] = r4.w;
+                }
+#pragma unroll
+                for (int c = 0; c < HALF; c += 4) {
+                    sum[c] = fmaf(sum[c], p.acc_scale, __shfl_sync(0xffffffffu, mine.x, c >> 2));
+                    sum[c + 1] = fmaf(sum[c + 1], p.acc_scale, __shfl_sync(0xffffffffu, mine.y, c >> 2));
+                    sum[c + 2] = fmaf(sum[c + 2], p.acc_scale, __shfl_sync(0xffffffffu, mine.z, c >> 2));
+                    sum[c + 3] = fmaf(sum[c + 3], p.acc_scale, __shfl_sync(0xffffffffu, mine.w, c >> 2));
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < HALF; c += 4) {
+                    sum[c] = __shfl_sync(0xffffffffu, mine.x, c >> 2);
+                    sum[c + 1] = __shfl_sync(0xffffffffu, mine.y, c >> 2);
+                    sum[c + 2] = __shfl_sync(0xffffffffu, mine.z, c >> 2);
+                    sum[c + 3] = __shfl_sync(0xffffffffu, mine.w, c >> 2);
                 }
             }
-            // the accumulators hold (A W^T) * acc_scale (operands are power-of-two scaled fp16 pairs): the running sums live
-            // in that domain (exact), the tile epilogue scales back
-#pragma unroll
-            for (int c = 0; c < HALF; ++c) sum[c] *= p.acc_scale;
+            if (p.prof) t_bias += clock64() - b0;
+            if (p.prof) { const long long n = clock64(); t_pro += n - e0; e0 = n; }
             for (int g = 0; g < num_groups; ++g) {
                 mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                if (p.prof) { const long long n = clock64(); t_tfull += n - e0; e0 = n; }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN_MAX + half * HALF;
 #pragma unroll
@@ -411,7 +452,9 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     else mbar_arrive(bar_tempty + 8 * acc);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (p.prof) { const long long n = clock64(); t_drain += n - e0; e0 = n; }
             }
+            const float4 bias_nxt = bias_of(it + 1);      // lands while this tile is written out
             if (p.tma_store) {
                 // ---- finish the values in place ...
                 const bool row_ok = row < p.n_rows;
@@ -441,8 +484,10 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 // beyond the tensor, so ragged tiles need no guards
                 const int row0 = tm * BM + q * 32;
                 auto stage_begin = [&]() -> uint4* {
+                    const long long w0 = p.prof ? clock64() : 0;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the chunk before last has left
                     __syncwarp();
+                    if (p.prof) t_wait += clock64() - w0;
                     return reinterpret_cast<uint4*>(stg_gen + stg_buf * LIN_STG_BYTES) + lane * 8;
                 };
                 auto stage_end = [&](const CUtensorMap* map, int c0) {
@@ -451,6 +496,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                     if (lane == 0) tma_store_2d(map, stg_u32 + stg_buf * LIN_STG_BYTES, c0, row0);
                     stg_buf ^= 1;
                 };
+                const long long y0 = p.prof ? clock64() : 0;
                 if (p.y) {
 #pragma unroll
                     for (int ch = 0; ch < HALF / 32; ++ch) {
@@ -479,6 +525,8 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         stage_end(&map_y, col0);
                     }
                 }
+                const long long y1 = p.prof ? clock64() : 0;
+                if (p.prof) t_y += y1 - y0;
                 if (p.y_hi) {
 #pragma unroll
                     for (int ch = 0; ch < HALF / 64; ++ch) {
@@ -486,14 +534,15 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         if (64 * ch + half * HALF >= p.BN || col0 >= p.N || col0 >= p.split_n) continue;
                         const int tail = p.BN - half * HALF - 64 * ch;     // < 64: chunk straddles the tile's right edge -> narrow chunk
                         const bool is_tail = tail < 64;
-                        // both halves of the pair are formed once and staged in the warp's two chunks at the same time
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        __syncwarp();
+                        // both halves of the pair are formed once -- in registers, BEFORE waiting for the staging chunks: the previous
+                        // chunk's TMA stores read them out meanwhile (the wait used to sit in front of the conversions and
+                        // serialised store latency and arithmetic, twice per tile) -- and staged in the warp's two chunks
                         // full chunk: [32][128 B] swizzled; tail chunk: [32][2 * tail B] plain row-major (tail = 16, 32 or 48 columns)
                         const int pieces = is_tail ? tail >> 3 : 8;         // 16-byte pieces per row
                         uint4* dh = reinterpret_cast<uint4*>(stg_gen) + lane * pieces;
                         uint4* dl = reinterpret_cast<uint4*>(stg_gen + LIN_STG_BYTES) + lane * pieces;
                         float amax = 0.0f;
+                        uint4 vh[8], vl[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             __half2 h2[4], l2[4];
@@ -507,10 +556,19 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                 const float2 hf = __half22float2(h2[e]);
                                 l2[e] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
                             }
+                            vh[j] = *reinterpret_cast<const uint4*>(h2);
+                            vl[j] = *reinterpret_cast<const uint4*>(l2);
+                        }
+                        const long long w0 = p.prof ? clock64() : 0;
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                        if (p.prof) t_wait += clock64() - w0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
                             if (j < pieces) {
                                 const int slot = is_tail ? j : (j ^ (lane & 7));
-                                dh[slot] = *reinterpret_cast<const uint4*>(h2);
-                                dl[slot] = *reinterpret_cast<const uint4*>(l2);
+                                dh[slot] = vh[j];
+                                dl[slot] = vl[j];
                             }
                         }
                         if (row_ok && !(amax <= 65000.0f)) flag |= 4;
@@ -523,6 +581,7 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                         stg_buf = 0;
                     }
                 }
+                if (p.prof) t_pair += clock64() - y1;
             } else if (p.cx) {
                 // ---- affine / additive coupling (coupling.py:212-269 of the reference) on the parameters held in registers:
                 // y_j = x_j * s_j + t_j (inverse: (x_j - t_j) / s_j), log|det| += +-sum_j log s_j
@@ -618,6 +677,13 @@ linear_f16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 }
             }
             __syncwarp();
+            bias_cur = bias_nxt;
+            if (p.prof) t_out += clock64() - e0;
+        }
+        if (p.prof && warp == 4 && lane == 0) {
+            long long* o = p.prof + (size_t)blockIdx.x * 16;
+            o[3] = clock64() - e_begin; o[4] = t_tfull; o[5] = t_drain; o[6] = t_out; o[7] = t_pro;
+            o[8] = t_bias; o[9] = t_wait; o[10] = t_y; o[11] = t_pair;
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive its stores
         if (flag && p.flags) atomicOr(p.flags, flag);
@@ -886,6 +952,7 @@ static int linear_f16x3_launch(const void* a_hi_, const void* a_lo_, int64_t lda
     p.ldr = ldr; p.ldy = ldy; p.lds = lds; p.n_rows = n_rows; p.K = in_features; p.N = out_features;
     p.relu_out = relu_out; p.split_relu = split_relu;
     p.y_first_col = y_first_col > 0 ? y_first_col : 0;
+    { const char* e = getenv("NFK_LINEAR_PROF"); p.prof = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     p.cx = nullptr; p.cy = nullptr; p.c_cols = nullptr; p.c_lad = nullptr; p.ldcx = p.ldcy = 0;
     p.c_col0 = p.c_dt = p.c_mult = p.c_act = p.c_inverse = 0;
     if (ce) {
