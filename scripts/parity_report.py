@@ -22,6 +22,21 @@ def line(name, got, ref32, truth):
         name, rel_err(got.cpu(), truth), rel_err(ref32, truth), rel_err(got.cpu(), ref32)))
 
 
+def tail(name, got, ref32, truth):
+    """Error percentiles of the deliberately sharp-bin stress vectors: what tests/test_native_parity.py's
+    assert_statistically_as_accurate bounds (p99 / p99.9 within 2x, worst element within a small multiple of the reference's)."""
+    def errs(a):
+        a, b = a.double().cpu().flatten(), truth.double().flatten()
+        fin = torch.isfinite(a) & torch.isfinite(b)
+        e = (a[fin] - b[fin]).abs() / torch.maximum(torch.maximum(a[fin].abs(), b[fin].abs()), torch.ones_like(b[fin]))
+        return e.sort().values
+    e, r = errs(got), errs(ref32)
+    n = len(e)
+    q = lambda v, f: float(v[min(n - 1, int(f * n))])
+    print("{:44s} native p99 {:.2e} p99.9 {:.2e} max {:.2e} | reference p99 {:.2e} p99.9 {:.2e} max {:.2e} | max ratio {:.2f}".format(
+        name, q(e, 0.99), q(e, 0.999), float(e[-1]), q(r, 0.99), q(r, 0.999), float(r[-1]), float(e[-1]) / max(float(r[-1]), 1e-30)))
+
+
 def dbl(sd):
     return {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
 
@@ -38,6 +53,15 @@ def main():
         wy, wl = g["tails_inv%d" % inv]
         line("spline tails inv=%d  y" % inv, y, wy, ty)
         line("spline tails inv=%d  lad" % inv, l, wl, tl)
+        tail("  stress tails inv=%d y" % inv, y, wy, ty)
+        tail("  stress tails inv=%d lad" % inv, l, wl, tl)
+        box = dict(left=-1.0, right=3.0, bottom=-1.0, top=3.0, min_bin_width=1e-2, min_bin_height=2e-2, min_derivative=5e-2)
+        for key, xin, kw in (("constrained_inv%d", g["x_constrained"], {}), ("constrained_box_inv%d", g["x_constrained"] * 4 - 1, box)):
+            yc, lc = rq.rational_quadratic_spline(xin.to(dev), g["uw"].to(dev), g["uh"].to(dev), g["ud_constrained"].to(dev), inverse=inv, **kw)
+            wyc, wlc = g[key % inv]
+            tyc, tlc = O.rq_spline(xin.double(), g["uw"].double(), g["uh"].double(), g["ud_constrained"].double(), inverse=inv, **kw)
+            tail("  stress %s y" % (key % inv), yc, wyc, tyc)
+            tail("  stress %s lad" % (key % inv), lc, wlc, tlc)
     g = load_golden("cfg2_rq_coupling")
     t = recipes.rq_coupling_layer()
     t.load_state_dict(g["sd"])
