@@ -69,13 +69,14 @@ def assert_statistically_as_accurate(got, ref32, truth, what):
     """Stress vectors with deliberately sharp bins are ill-conditioned next to knots (a 1-ulp knot difference moves
     theta by percents), so ANY fp32 evaluation has a heavy error tail there and the single worst element is luck.
     Criterion: the error distribution against the fp64 truth must match the reference's: 99th / 99.9th percentile
-    within 2x (+1e-5), worst element within 30x of the reference's worst (profiles/parity_calibration_r1.txt)."""
+    within 2x (+1e-5), worst element within 15x of the reference's worst (profiles/parity_calibration_r2.txt, captured with
+    the shipped kernels: the largest observed ratio is 10.1, on the log|det| of the sharpest constrained-spline vectors)."""
     e, r = _elementwise_err(got, truth), _elementwise_err(ref32, truth)
     n = len(e)
     for q in (0.99, 0.999):
         i = min(n - 1, int(q * n))
         assert e[i] <= 2 * r[i] + TOL, (what, q, float(e[i]), float(r[i]))
-    assert e[-1] <= 30 * r[-1] + TOL, (what, "max", float(e[-1]), float(r[-1]))
+    assert e[-1] <= 15 * r[-1] + TOL, (what, "max", float(e[-1]), float(r[-1]))
 
 
 @torch.no_grad()
