@@ -53,7 +53,7 @@ constexpr int STEP_G2_STAGES = 3;
 constexpr int STEP_G2_STAGE_BYTES = 24576;
 constexpr int STEP_G2_LO_OFF = 12288;
 constexpr int STEP_BN_MAX = 192;                                     // widest final-layer column tile
-constexpr int STEP_NBAR = 5;                                         // ring barriers (max stages of any geometry)
+constexpr int STEP_NBAR = 6;                                         // ring barriers (max stages of any geometry)
 constexpr int STEP_BAR_OFF = STEP_R_BYTES + STEP_RING_BYTES;
 constexpr int STEP_BIAS_OFF = STEP_BAR_OFF + 256;                    // [2][192] fp32 packed bias of the current / next column tile
 constexpr int STEP_Y_OFF = STEP_BIAS_OFF + 2 * STEP_BN_MAX * 4;      // 3 x 4 KB output staging (128-byte aligned)
@@ -112,6 +112,9 @@ struct StepParams {
     int drain_t;                  // K-slabs accumulated in TMEM per partial sum of a trunk layer (DRAIN_SLABS_LINEAR by default)
     int drain_f;                  // K-slabs accumulated in TMEM per partial sum of the final layer (DRAIN_SLABS_FUSED, or all)
     uint32_t zero;                // always 0 (mbar_arrive_after_loads)
+    int k16;                      // NFK_STEP_K16=1 (experiment, off): final-layer weights stream as SIX stages of one K = 16 step each
+                                  // (SWIZZLE_32B rows) instead of three K = 32 slabs -- same 72 KB of ring, 5/6 instead of 2/3 of it in
+                                  // flight; correct, but 9 % slower (32-byte TMA rows / twice the barrier traffic)
     int tma_x;                    // inputs of the transformed features arrive as TMA boxes (consecutive columns, 16-byte aligned)
     float out_scale;
     float* lad_accum;
@@ -148,13 +151,14 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t ring = smem_base + STEP_R_BYTES;
     const uint32_t bars = smem_base + STEP_BAR_OFF;
-    const uint32_t bar_full = bars, bar_empty = bars + 40;
-    const uint32_t bar_tfull = bars + 80, bar_tempty = bars + 96;
-    const uint32_t bar_aready = bars + 112;       // the epilogue warps have written the next layer's operand into R
-    const uint32_t bar_outready = bars + 120;     // trunk_only: ... the trunk's output, ready for the TMA stores
-    const uint32_t bar_bfull = bars + 128, bar_bempty = bars + 144;
-    const uint32_t bar_xfull = bars + 160, bar_xempty = bars + 176;      // the two TMA-staged input tiles (tma_x)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STEP_BAR_OFF + 200);
+    const uint32_t bar_full = bars, bar_empty = bars + 8 * STEP_NBAR;
+    const uint32_t bar_tfull = bars + 16 * STEP_NBAR, bar_tempty = bar_tfull + 16;
+    const uint32_t bar_aready = bar_tfull + 32;   // the epilogue warps have written the next layer's operand into R
+    const uint32_t bar_outready = bar_tfull + 40; // trunk_only: ... the trunk's output, ready for the TMA stores
+    const uint32_t bar_bfull = bar_tfull + 48, bar_bempty = bar_tfull + 64;
+    const uint32_t bar_xfull = bar_tfull + 80, bar_xempty = bar_tfull + 96;      // the two TMA-staged input tiles (tma_x)
+    static_assert(16 * STEP_NBAR + 112 + 8 <= 248, "barrier block");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STEP_BAR_OFF + 248);
     // [2][128 rows][TF] fp32 input tiles in the tail of the ring region, which the final layer's geometry (G2) leaves unused
     constexpr int X_TILE_OFF = STEP_R_BYTES + STEP_G2_STAGES * STEP_G2_STAGE_BYTES;
     static_assert(X_TILE_OFF + 2 * BM * 8 * 4 <= STEP_R_BYTES + STEP_RING_BYTES, "input tiles must fit behind the G2 stages");
@@ -300,6 +304,26 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                                              bar_bfull + 8 * bslot);
                                 if (++bslot == 2) { bslot = 0; bphase ^= 1; }
                             }
+                            if (p.k16) {
+                                // six half-slab stages: [BN rows][32 bytes] hi, then lo (6 KB each at BN = 192)
+                                for (int kh = 0; kh < 2 * num_kh; ++kh) {
+                                    slot_wait(s);
+                                    const uint32_t full = bar_full + 8 * s;
+                                    const uint32_t sw = ring + s * (STEP_G2_STAGE_BYTES / 2);
+                                    mbar_expect_tx(full, tx / 2);
+                                    if (CL == 1) {
+                                        tma_load_2d(sw, &map_wf_hi, full, kh * 16, n * BN);
+                                        tma_load_2d(sw + BN * 32, &map_wf_lo, full, kh * 16, n * BN);
+                                    } else {
+                                        const uint32_t off = (uint32_t)(cta_rank * wrows) * 32u;
+                                        tma_load_2d_multicast(sw + off, &map_wf_hi, full, kh * 16, n * BN + cta_rank * wrows, cl_mask);
+                                        tma_load_2d_multicast(sw + BN * 32 + off, &map_wf_lo, full, kh * 16, n * BN + cta_rank * wrows, cl_mask);
+                                    }
+                                    uses ^= 1u << s;
+                                    if (++s == 2 * STEP_G2_STAGES) s = 0;
+                                }
+                                continue;
+                            }
                             for (int ks = 0; ks < num_kh; ++ks) {
                                 slot_wait(s);
                                 const uint32_t full = bar_full + 8 * s;
@@ -429,10 +453,29 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                     for (int n = 0; n < p.num_n_tiles; ++n) {
                         for (int g = 0; g < groupsf; ++g, ++gc) {
                             const int slabs = min(drain_f, num_kh - g * drain_f);
-                            if (!solo && (int)(gc & 1u) != my) { pass(s, slabs, STEP_G2_STAGES); continue; }
+                            if (!solo && (int)(gc & 1u) != my) { pass(s, p.k16 ? 2 * slabs : slabs, p.k16 ? 2 * STEP_G2_STAGES : STEP_G2_STAGES); continue; }
                             const int acc = gc & 1u;
                             mbar_wait(bar_tempty + 8 * acc, ((gc >> 1) & 1u) ^ 1u);
                             const uint32_t d_tmem = tmem_base + acc * BN_MAX;
+                            if (p.k16) {
+                                // one stage per K = 16 step: cross terms, main product, release
+                                for (int j = 0; j < 2 * slabs; ++j) {
+                                    full_wait(s);
+                                    tc_fence_after();
+                                    const uint32_t sa = smem_base + (g * drain_f + (j >> 1)) * STEP_SLAB_BYTES;
+                                    const uint32_t sw = ring + s * (STEP_G2_STAGE_BYTES / 2);
+                                    const uint64_t adv = (uint64_t)((j & 1) * 2);          // second K step of the resident 64-byte rows
+                                    const uint64_t a_hi = make_smem_desc(sa) + adv, a_lo = make_smem_desc(sa + A_BYTES) + adv;
+                                    const uint64_t w_hi = make_smem_desc_k16(sw), w_lo = make_smem_desc_k16(sw + BN * 32);
+                                    if (leader) umma_f16(d_tmem, a_lo, w_hi, idescf, j != 0);
+                                    if (leader) umma_f16(d_tmem, a_hi, w_lo, idescf, 1);
+                                    if (leader) umma_f16(d_tmem, a_hi, w_hi, idescf, 1);
+                                    release(s);
+                                    if (++s == 2 * STEP_G2_STAGES) s = 0;
+                                }
+                                if (leader) umma_commit(bar_tfull + 8 * acc);
+                                continue;
+                            }
                             for (int j = 0; j < slabs; ++j) {
                                 full_wait(s);
                                 tc_fence_after();
@@ -794,8 +837,14 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
         if ((rc = make_map(&mh_lo, (const __half*)d->h_lo, p.n_rows, H, d->ldh, BM))) return rc;
     } else {
         const int packed_rows = p.d_t * Cfg::MP;
-        if ((rc = make_map(&mwf_hi, (const __half*)d->wp_hi, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
-        if ((rc = make_map(&mwf_lo, (const __half*)d->wp_lo, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
+        { const char* e = getenv("NFK_STEP_K16"); p.k16 = (e && e[0] == '1') ? 1 : 0; }      // measured slower (168.7 vs 155.2 ms per step): off
+        if (p.k16) {
+            if ((rc = make_map_k16(&mwf_hi, (const __half*)d->wp_hi, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
+            if ((rc = make_map_k16(&mwf_lo, (const __half*)d->wp_lo, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
+        } else {
+            if ((rc = make_map(&mwf_hi, (const __half*)d->wp_hi, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
+            if ((rc = make_map(&mwf_lo, (const __half*)d->wp_lo, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
+        }
         p.num_n_tiles = (p.d_t + Cfg::TF - 1) / Cfg::TF;
         p.tma_y = (p.y && !p.t_cols && p.t_col0 % 4 == 0 && p.ldy % 4 == 0 && aligned16(p.y)) ? 1 : 0;
         // inputs as TMA boxes of TF columns: consecutive columns from a 16-byte aligned first column (tiles start at multiples of TF >= 4 floats...

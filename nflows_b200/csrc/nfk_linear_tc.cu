@@ -831,6 +831,21 @@ int make_map(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t 
     return NFK_OK;
 }
 
+// K-major operand tile of 16 halfs (one UMMA K step) per row: 32-byte rows, SWIZZLE_32B (the coupling-step kernel's final layer)
+int make_map_k16(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NFK_E_CUDA, "cuTensorMapEncodeTiled (k16) failed with CUresult %d", (int)r);
+    return NFK_OK;
+}
+
 int sm_count() {
     static std::atomic<int> counts[64];                      // per device
     int dev = 0;

@@ -81,11 +81,14 @@ __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtens
 // Hands a TMA-filled shared-memory slot back to its producer AFTER this warp's loads from it have returned.  mbarrier.arrive
 // is not ordered behind earlier LDS of the same warp (ptxas schedules it two instructions after the last LDS.128 and the barrier
 // unit does not wait for the load queue), so the producer's next bulk copy could overwrite the slot under a load still queued:
-// measured on hardware (r2) as the last float4 of a warp's bias window holding the bias of column tile n+2.  Two guards:
-// the generic->async proxy fence, and a true data dependency -- the barrier address is offset by (loaded bits & zero), `zero`
-// a kernel parameter that is always 0, which ptxas cannot fold away.
+// measured on hardware (r2) as the last float4 of a warp's bias window holding the bias of column tile n+2.  The guard is a
+// true data dependency -- the barrier address is offset by (loaded bits & zero), `zero` a kernel parameter that is always 0,
+// which ptxas cannot fold away: the arrive cannot issue before the loaded registers exist, i.e. before shared memory was read.
+// (A generic->async proxy fence in front of it as well costs ~1 000 cycles per use: two per column tile and warp.)
 __device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t loaded_bits, uint32_t zero) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#ifdef NFK_RELEASE_WITH_PROXY_FENCE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // r2 first fix: dependency AND fence (~1 000 cycles per fence)
+#endif
     mbar_arrive(bar + (loaded_bits & zero));
 }
 
@@ -222,6 +225,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * ROW_BYTES) >> 4) << 32) | (1ull << 46) |
            ((uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61);
 }
+// K-major operand with 32-byte rows (one K = 16 step of fp16), SWIZZLE_32B (layout type 6): 8-row groups are 256 bytes apart
+__device__ __forceinline__ uint64_t make_smem_desc_k16(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * 32) >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=b=F16 (format 0 at [7,10) and [10,13)), K-major both, N>>3 at [17,23),
 // M>>4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc(int bn, int m = BM) {
@@ -240,6 +247,7 @@ __device__ __forceinline__ void split_f16(float v, float scale, __half& hi, __ha
 
 // host helpers (nfk_linear_tc.cu)
 int make_map(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t ld, int box_rows);
+int make_map_k16(CUtensorMap* map, const __half* base, int64_t rows, int K, int64_t ld, int box_rows);
 int make_out_map(CUtensorMap* map, float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
 int make_out_map16(CUtensorMap* map, __half* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
 int sm_count();
