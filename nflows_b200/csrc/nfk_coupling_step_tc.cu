@@ -112,6 +112,7 @@ struct StepParams {
     int drain_t;                  // K-slabs accumulated in TMEM per partial sum of a trunk layer (DRAIN_SLABS_LINEAR by default)
     int drain_f;                  // K-slabs accumulated in TMEM per partial sum of the final layer (DRAIN_SLABS_FUSED, or all)
     uint32_t zero;                // always 0 (mbar_arrive_after_loads)
+    int x_prefetch;               // NFK_STEP_X_PREFETCH=1: TMA-prefetch a row block's input tiles into L2 before its final phase
     int k16;                      // NFK_STEP_K16=1 (experiment, off): final-layer weights stream as SIX stages of one K = 16 step each
                                   // (SWIZZLE_32B rows) instead of three K = 32 slabs -- same 72 KB of ring, 5/6 instead of 2/3 of it in
                                   // flight; correct, but 9 % slower (32-byte TMA rows / twice the barrier traffic)
@@ -283,6 +284,14 @@ rq_coupling_step_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __gr
                         continue;
                     }
                     // ---- G2: final layer, one stage = one K-slab of one column tile
+                    if (p.tma_x && p.x_prefetch) {
+                        // the row block's input tiles towards L2 now (each is 128 separate 32-byte row segments of HBM): their TMA
+                        // loads below then hit L2 instead of sitting in the TMA queue in front of the weight stages for a DRAM latency
+                        for (int n = 0; n < p.num_n_tiles; ++n)
+                            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(&map_x)),
+                                         "r"(p.t_col0 + n * TF), "r"(m0)
+                                         : "memory");
+                    }
                     drain();
                     {
                         constexpr uint32_t tx = 2u * (uint32_t)BN * ROW_BYTES;
@@ -837,6 +846,7 @@ static int launch_step(const NfkCouplingStep* d, StepParams& p, cudaStream_t st)
         if ((rc = make_map(&mh_lo, (const __half*)d->h_lo, p.n_rows, H, d->ldh, BM))) return rc;
     } else {
         const int packed_rows = p.d_t * Cfg::MP;
+        { const char* e = getenv("NFK_STEP_X_PREFETCH"); p.x_prefetch = (e && e[0] == '1') ? 1 : 0; }
         { const char* e = getenv("NFK_STEP_K16"); p.k16 = (e && e[0] == '1') ? 1 : 0; }      // measured slower (168.7 vs 155.2 ms per step): off
         if (p.k16) {
             if ((rc = make_map_k16(&mwf_hi, (const __half*)d->wp_hi, packed_rows, H, d->ldwp, Cfg::BN / CL))) return rc;
