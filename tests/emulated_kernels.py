@@ -206,6 +206,40 @@ def install(monkeypatch):
         y[:, t] = yt
         return y
 
+    def rq_coupling_step_supported(num_bins, tails, hidden, in_features, num_square_layers):
+        # the predicate of nfk_rq_coupling_step_supported (csrc/nfk_coupling_step_tc.cu)
+        return (num_bins in (4, 8, 10, 16) and 32 <= hidden <= 256 and hidden % 32 == 0 and in_features >= 8 and in_features % 8 == 0
+                and 0 <= num_square_layers < 9)
+
+    def rq_coupling_step(plan, a, desc=None, inverse=False, wp=None, bias_packed=None, x=None, t_cols=None, y=None, lad_accum=None,
+                         flags=None, y_pair=None, h_pair=None):
+        """The layer recursion of include/nfk.h (nfk_rq_coupling_step_f16x3) on the operands a dense.StepPlan packs: flag bit 0
+        relu on (acc + bias), bit 1 add the current skip tensor, bit 2 the fp32 result becomes the skip tensor, bit 3 the next
+        consumer sees relu(.); every hidden activation goes through the fp16 pair at the plan's exponent."""
+        count("rq_coupling_step" if h_pair is None else "trunk_step")
+        hdim = plan.hidden
+        cur, skip = _value(a), None
+        for l, f in enumerate(plan.layer_flags):
+            if l == 0:
+                w = _value(plan.w0)
+            else:
+                blk = slice((l - 1) * hdim, l * hdim)
+                w = _value(K.Pair16(plan.wt_hi[blk], plan.wt_lo[blk], int(plan.wt_exps_c[l - 1])))
+            v = cur @ w.t() + plan.bias[l * hdim:(l + 1) * hdim].double()
+            if f & 1:
+                v = F.relu(v)
+            if f & 2:
+                v = v + skip
+            v = v.float().double()                      # the kernel's sums are fp32
+            if f & 4:
+                skip = v
+            cur = _value(_pair(v.float(), plan.act_exp, relu=bool(f & 8)))
+        if h_pair is not None:
+            _pair(cur.float(), plan.act_exp, False, h_pair)
+            return None
+        return rq_coupling_final(desc, inverse, _pair(cur.float(), plan.act_exp), wp, bias_packed, x, t_cols, y, lad_accum, flags,
+                                 y_pair=y_pair)
+
     def affine_coupling_rows(x, params, mult, scale_activation, inverse, t_cols, id_cols, lad_accum, out=None):
         count("affine_coupling_rows")
         y = torch.empty_like(x) if out is None else out
@@ -249,7 +283,8 @@ def install(monkeypatch):
             nchw_to_rows=nchw_to_rows, rows_to_nchw=rows_to_nchw, squeeze_rows=squeeze_rows, im2col3x3=im2col3x3,
             segment_sum_=segment_sum_, f16x3_supported=f16x3_supported, linear_f16x3=linear_f16x3,
             rq_coupling_final_supported=rq_coupling_final_supported, rq_coupling_final_padded_params=rq_coupling_final_padded_params,
-            rq_coupling_final=rq_coupling_final, affine_coupling_final=affine_coupling_final, affine_coupling_rows=affine_coupling_rows, rq_coupling_step_supported=lambda *a: False,
+            rq_coupling_final=rq_coupling_final, affine_coupling_final=affine_coupling_final, affine_coupling_rows=affine_coupling_rows,
+            rq_coupling_step_supported=rq_coupling_step_supported, rq_coupling_step=rq_coupling_step,
             residual_trunk_supported=lambda *a: False).items():
         monkeypatch.setattr(K, name, fn)
     return calls

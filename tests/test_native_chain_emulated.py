@@ -149,3 +149,65 @@ def test_affine_flow_behind_folded_affine_runs(emu):
     lp = flow.log_prob(r["x"])
     assert emu.get("affine_coupling_final", 0) == 3 and emu.get("gather_cols", 0) <= 2
     assert rel_err(lp, r["log_prob_fp64"]) <= max(TOL, 3 * rel_err(r["log_prob"], r["log_prob_fp64"]))
+
+
+@pytest.fixture
+def emu_step(monkeypatch):
+    monkeypatch.setattr(config, "coupling_step_kernel", True)
+    return emulated_kernels.install(monkeypatch)
+
+
+@torch.no_grad()
+def test_flow_on_the_one_kernel_coupling_step(emu_step):
+    """Row ns1's host side: dense.plan_step_kernel / StepPlan (stacked weight pairs, per-layer exponents, layer flags) and the
+    pair hand-off between the affine GEMM and the step kernel, against the fp64 torch formulation."""
+    torch.manual_seed(0)
+    flow = recipes.perturb_(recipes.rq_nsf(32, hidden_features=32, num_layers=3)).eval()
+    x = torch.randn(300, 32)
+    want = [t.float() for t in flow.double()._transform(x.double())]
+    flow.float()
+    config.coupling_block_rows, saved = 128, config.coupling_block_rows
+    try:
+        got = flow._transform(x)
+    finally:
+        config.coupling_block_rows = saved
+    assert emu_step.get("rq_coupling_step", 0) == 9 and emu_step.get("trunk_step", 0) == 0      # 3 couplings x 3 row blocks
+    assert emu_step.get("linear_f16x3", 0) == 3                                                   # only the folded affine runs
+    assert rel_err(got[0], want[0]) <= TOL and rel_err(got[1], want[1]) <= TOL
+
+
+@torch.no_grad()
+def test_autoregressive_transform_on_the_step_kernel(emu_step):
+    """Row f1's host side (BASELINE cfg 4): forward = one step launch on the masked MADE weights; inverse = one launch per degree
+    prefix on the degree-sorted sub-network (_sorted_subnets), against the reference golden ar_rq.pt."""
+    g = load_golden("ar_rq")
+    torch.manual_seed(g["seed"])
+    ar = T.MaskedPiecewiseRationalQuadraticAutoregressiveTransform(features=64, hidden_features=256, num_bins=8, tails="linear",
+                                                                   tail_bound=3.0, num_blocks=2).eval()
+    for name, p in ar.named_parameters():
+        if "final_layer" in name:
+            p.mul_(g["final_scale"])
+    x = g["x"][:96]
+    y, lad = ar(x)
+    assert emu_step.get("rq_coupling_step", 0) == 1
+    assert rel_err(y, g["y_fp64"][:96]) <= max(TOL, 3 * rel_err(g["y"][:96], g["y_fp64"][:96]))
+    assert rel_err(lad, g["lad_fp64"][:96]) <= max(3e-5, 3 * rel_err(g["lad"][:96], g["lad_fp64"][:96]))
+    xi, li = ar.inverse(x)
+    assert emu_step.get("rq_coupling_step", 0) == 1 + 64                                          # one launch per feature
+    assert rel_err(xi, g["xinv_fp64"][:96]) <= max(1e-4, 3 * rel_err(g["xinv"][:96], g["xinv_fp64"][:96]))
+    assert rel_err(li, g["ladinv_fp64"][:96]) <= max(1e-3, 3 * rel_err(g["ladinv"][:96], g["ladinv_fp64"][:96]))
+
+
+@torch.no_grad()
+def test_affine_coupling_trunk_as_one_step_launch(emu_step):
+    """Row ns2's host side: the conditioner trunk of an affine coupling is the step kernel stopped after its last trunk layer."""
+    r = load_golden("affine_rows")["default48"]
+    from nflows_b200.nn.nets import ResidualNet
+    from nflows_b200.utils import torchutils
+    t = T.AffineCouplingTransform(torchutils.create_alternating_binary_mask(48),
+                                  lambda i, o: ResidualNet(i, o, hidden_features=64, num_blocks=2)).eval()
+    t.load_state_dict(r["sd"], strict=True)
+    y, lad = t(r["x"])
+    assert emu_step.get("trunk_step", 0) == 1 and emu_step.get("affine_coupling_final", 0) == 1 and emu_step.get("linear_f16x3", 0) == 0
+    assert rel_err(y, r["y_fp64"].float()) <= max(TOL, 3 * rel_err(r["y"], r["y_fp64"].float()))
+    assert rel_err(lad, r["lad_fp64"].float()) <= max(TOL, 3 * rel_err(r["lad"], r["lad_fp64"].float()))
