@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NFK_ABI_VERSION 4
+#define NFK_ABI_VERSION 5
 
 #define NFK_OK 0
 #define NFK_E_INVALID (-1)   /* bad argument (shape, alignment, unsupported size) */
@@ -132,23 +132,6 @@ int nfk_glu_skip_rows(const float* t, int64_t ldt, const float* gate, int64_t ld
                       int64_t ldy, void* y_hi, void* y_lo, int64_t lds, int32_t y_exp, int split_relu, int64_t n_rows,
                       int32_t n_cols, int32_t* flags, void* stream);
 
-/* EXPERIMENTAL (not yet validated on hardware; the host code uses it only when NFLOWS_B200_TRUNK_KERNEL=1).
- * The square layers of a conditioner trunk (the residual blocks of ResidualNet, nn/nets/resnet.py:9-55) as ONE persistent
- * kernel: h_{l+1} = post_l(pre_l(h_l) W_l^T + b_l) [+ skip], l = 0..num_layers-1, every W_l hidden x hidden, the
- * activation pair of a 128-row tile resident in shared memory between layers.
- *   a_hi/a_lo : fp16 pair (exponent act_exp) of pre_0(h_0) [n_rows, hidden]
- *   w_hi/w_lo : fp16 pairs of the layers' weights stacked row-wise [num_layers * hidden, hidden], layer l with exponent
- *               w_exps[l] (HOST array);  bias: fp32 [num_layers * hidden]
- *   layer_flags (HOST array): bit 0 relu on (acc + bias); bit 1 add the current skip tensor (skip_in until a layer with
- *               bit 2 has run, skip_buf afterwards); bit 2 the fp32 result is a later layer's skip tensor (written to skip_buf);
- *               bit 3 the consumer of this layer's output applies relu to its input (the written pair is of relu(.))
- *   y_hi/y_lo : fp16 pair (exponent act_exp) of the last layer's output, pre-activated per its bit 3 */
-int nfk_residual_trunk_f16x3_supported(int32_t hidden_features, int32_t num_layers, int64_t lda, int64_t ldw);
-int nfk_residual_trunk_f16x3(const void* a_hi, const void* a_lo, int64_t lda, int32_t act_exp, const void* w_hi,
-                             const void* w_lo, int64_t ldw, const int32_t* w_exps, const float* bias,
-                             const int32_t* layer_flags, int32_t num_layers, const float* skip_in, float* skip_buf,
-                             int64_t ld_skip, void* y_hi, void* y_lo, int64_t lds, int64_t n_rows, int32_t hidden_features,
-                             int32_t* flags, void* stream);
 
 /* ---- fused RQ-coupling step ------------------------------------------------------------------------------------ */
 /* Final conditioner layer + spline + scatter + log|det| in ONE tcgen05 kernel: replaces the last F.linear of the
@@ -188,8 +171,8 @@ int nfk_rq_coupling_final_f16x3(const NfkSplineDesc* desc, int inverse, const vo
  *   wt_hi/wt_lo : pairs of the num_square_layers hidden x hidden weights stacked row-wise, layer l with exponent wt_exps[l]
  *                 (HOST array); may be NULL when num_square_layers == 0
  *   bias_trunk  : fp32 [(1 + num_square_layers) * hidden]
- *   layer_flags : HOST array [1 + num_square_layers], bits as in nfk_residual_trunk_f16x3 (1 relu on the output, 2 add the
- *                 saved skip tensor, 4 save the fp32 output as the skip tensor, 8 the next layer takes relu of this output)
+ *   layer_flags : HOST array [1 + num_square_layers], bits: 1 relu on the output (acc + bias), 2 add the
+ *                 saved skip tensor, 4 save the fp32 output as the skip tensor, 8 the next layer takes relu of this output
  *   act_exp     : exponent of every hidden activation pair
  *   wp_hi/wp_lo, bias_packed, x, t_cols, t_col0, d_t, y | (y_hi, y_lo, y_exp), lad_accum: as nfk_rq_coupling_final_f16x3
  *   h_hi/h_lo   : when non-NULL the kernel stops after the last trunk layer and writes that layer's output pair (exponent

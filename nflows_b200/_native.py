@@ -72,9 +72,6 @@ _SIGNATURES = {
                                                 c_int32, c_int32, c_int32, c_int, _P, c_int64, _P, c_int64, _P, _P]),
     "nfk_glu_skip_rows": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int, c_int64, c_int32,
                                   _P, _P]),
-    "nfk_residual_trunk_f16x3_supported": (c_int, [c_int32, c_int32, c_int64, c_int64]),
-    "nfk_residual_trunk_f16x3": (c_int, [_P, _P, c_int64, c_int32, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P, c_int64, _P, _P,
-                                         c_int64, c_int64, c_int32, _P, _P]),
     "nfk_rq_coupling_final_supported": (c_int, [c_int32, c_int32, c_int32, c_int64]),
     "nfk_rq_coupling_final_padded_params": (c_int32, [c_int32, c_int32]),
     "nfk_rq_coupling_final_f16x3": (c_int, [POINTER(NfkSplineDesc), c_int, _P, _P, c_int64, c_int32, _P, _P, c_int64, c_int32, _P,
@@ -113,8 +110,8 @@ def load():
         fn = getattr(lib, name)   # AttributeError here means header and library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.nfk_version() != 4:
-        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 4".format(lib.nfk_version()))
+    if lib.nfk_version() != 5:
+        raise NativeUnavailable("libnfk_sm100.so ABI version {} != 5".format(lib.nfk_version()))
     _lib = lib
     return lib
 

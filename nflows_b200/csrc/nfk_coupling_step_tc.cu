@@ -66,7 +66,7 @@ static_assert(STEP_G1_UNITS * STEP_G1_UNIT_BYTES <= STEP_RING_BYTES && STEP_G2_S
 static_assert(STEP_Y_OFF % 128 == 0, "staging alignment");
 static_assert(STEP_SMEM_BYTES <= 232448, "coupling-step kernel shared memory");
 
-// layer_flags bits (same meaning as nfk_residual_trunk_f16x3)
+// layer_flags bits (include/nfk.h: NfkCouplingStep)
 constexpr int SL_RELU_OUT = 1;     // relu on (acc + bias)
 constexpr int SL_ADD_SKIP = 2;     // + the saved skip tensor (never combined with SL_RELU_OUT)
 constexpr int SL_SAVE_SKIP = 4;    // the fp32 result is the skip tensor of a later layer

@@ -62,73 +62,6 @@ def chain_uses_tc(chain, first_in_features):
     return True
 
 
-_TRUNK_CACHE = {}
-
-
-def trunk_kernel_enabled():
-    """The persistent trunk kernel is experimental (round 1: not validated on hardware): opt in with NFLOWS_B200_TRUNK_KERNEL=1."""
-    return os.environ.get("NFLOWS_B200_TRUNK_KERNEL", "0") == "1"
-
-
-def plan_trunk_kernel(chain):
-    """Layer flags for nfk_residual_trunk_f16x3 over chain[1:-1] (every layer but the first and the last), or None when the
-    chain does not have that shape: square hidden layers, skip adds that follow the 'input of the layer two before' pattern
-    of ResidualNet, no relu between a skip add and its accumulate."""
-    body = chain[:-1]
-    if len(body) < 3:
-        return None
-    h = body[0][0].shape[0]
-    flags = []
-    current = 0                                  # index (in body) of the layer whose fp32 output is the current skip tensor
-    for i in range(1, len(body)):
-        weight, bias, relu_in, relu_out, residual = body[i]
-        if tuple(weight.shape) != (h, h) or bias is None or weight.stride(0) % 8:
-            return None
-        f = 0
-        if relu_out:
-            f |= 1
-        if residual == "skip":
-            if relu_out or i - 2 != current:
-                return None
-            f |= 2
-        elif residual is not None:
-            return None
-        if i + 2 < len(chain) and chain[i + 2][4] == "skip":
-            f |= 4
-            current = i
-        if chain[i + 1][2]:
-            f |= 8
-        flags.append(f)
-    if not K.residual_trunk_supported(h, len(flags), h, h):
-        return None
-    return flags
-
-
-def pack_trunk(body_tail):
-    """Stacked fp16 pairs, per-layer exponents and stacked biases of the layers the trunk kernel runs; cached per version."""
-    key = tuple(id(layer[0]) for layer in body_tail)
-    sig = tuple((layer[0].data_ptr(), layer[0]._version, layer[1].data_ptr(), layer[1]._version, str(layer[0].device))
-                for layer in body_tail) + (cache_epoch(),)
-    hit = _TRUNK_CACHE.get(key)
-    if hit is None or hit[0] != sig:
-        h = body_tail[0][0].shape[0]
-        dev = body_tail[0][0].device
-        w_hi = torch.empty(len(body_tail) * h, h, dtype=torch.float16, device=dev)
-        w_lo = torch.empty_like(w_hi)
-        exps = []
-        for l, (weight, bias, _, _, _) in enumerate(body_tail):
-            w = weight.detach().contiguous()
-            e = K.weight_exp(w)
-            K.split_f16(w, e, out=K.Pair16(w_hi[l * h:(l + 1) * h], w_lo[l * h:(l + 1) * h], e))
-            exps.append(e)
-        bias_all = torch.cat([layer[1].detach().reshape(-1).float() for layer in body_tail]).contiguous()
-        hit = (sig, (w_hi, w_lo, exps, bias_all), [layer[0] for layer in body_tail])
-        _TRUNK_CACHE[key] = hit
-        if len(_TRUNK_CACHE) > 256:
-            _TRUNK_CACHE.pop(next(iter(_TRUNK_CACHE)))
-    return hit[1]
-
-
 class StepPlan:
     """Operands of nfk_rq_coupling_step_f16x3 for every layer of a conditioner but the last: Pair16 of the initial layer's weight,
     stacked pairs + exponents of the square layers, stacked biases, layer flags."""
@@ -340,18 +273,6 @@ def _run_trunk_block(chain, x, id_cols, use_tc, last_out, x_pair, flags):
             out = last_out if last_out is not None else K.Pair16.empty(x_pair.shape[0], body[0][0].shape[0], act_exp(), x_pair.hi.device)
             with K.timed("trunk_step", x_pair.shape[0]):
                 K.rq_coupling_step(step_plan(chain), x_pair, h_pair=out, flags=flags)
-            return ChainState(pair=out)
-        trunk_flags = plan_trunk_kernel(chain) if trunk_kernel_enabled() else None
-        if trunk_flags is not None:
-            # first layer as a GEMM of its own (its K differs), everything up to the last layer in ONE persistent kernel
-            weight, bias, relu_in, relu_out, residual = body[0]
-            need_raw = any(f & 2 for f in trunk_flags)
-            y, pair = K.linear_f16x3(x_pair, split_weight(weight), bias.detach() if bias is not None else None,
-                                     relu_out=relu_out, want_y=need_raw, want_split=True, split_relu=chain[1][2], flags=flags)
-            w_hi, w_lo, exps, bias_all = pack_trunk(body[1:])
-            out = last_out if last_out is not None else K.Pair16.empty(pair.shape[0], pair.shape[1], pair.exp, pair.hi.device)
-            scratch = torch.empty_like(y) if any(f & 4 for f in trunk_flags) else None
-            K.residual_trunk(pair, w_hi, w_lo, exps, bias_all, trunk_flags, y, scratch, out, flags=flags)
             return ChainState(pair=out)
         ctx_pair = chain.context_pair(flags) if isinstance(chain, Chain) else None
         conv = getattr(chain, "conv3x3", ())

@@ -426,28 +426,6 @@ def linear_f16x3(a, w, bias=None, residual=None, relu_out=False, want_y=True, wa
     return y, pair
 
 
-def residual_trunk_supported(hidden, num_layers, lda, ldw):
-    return bool(N.load().nfk_residual_trunk_f16x3_supported(int(hidden), int(num_layers), int(lda), int(ldw)))
-
-
-def residual_trunk(a, w_hi, w_lo, w_exps, bias, layer_flags, skip_in, skip_buf, y_pair, flags=None):
-    """EXPERIMENTAL persistent trunk kernel (include/nfk.h: nfk_residual_trunk_f16x3): the square layers of a conditioner trunk in
-    one launch.  a, y_pair: Pair16 [n, H] with the same exponent; w_hi / w_lo: fp16 [L*H, H]; w_exps, layer_flags: int lists."""
-    n, h = a.shape
-    num_layers = len(layer_flags)
-    if y_pair.exp != a.exp:
-        raise ValueError("input and output pairs of the trunk kernel share one exponent")
-    exps = (ctypes.c_int32 * num_layers)(*[int(e) for e in w_exps])
-    lf = (ctypes.c_int32 * num_layers)(*[int(f) for f in layer_flags])
-    with timed("trunk_%dx%d" % (h, num_layers), n):
-        N.check(N.lib().nfk_residual_trunk_f16x3(
-            a.hi.data_ptr(), a.lo.data_ptr(), a.hi.stride(0), a.exp, w_hi.data_ptr(), w_lo.data_ptr(), w_hi.stride(0), exps,
-            bias.data_ptr(), lf, num_layers, N.ptr(skip_in), N.ptr(skip_buf),
-            skip_in.stride(0) if skip_in is not None else (skip_buf.stride(0) if skip_buf is not None else 0),
-            y_pair.hi.data_ptr(), y_pair.lo.data_ptr(), y_pair.hi.stride(0), n, h, N.ptr(flags), N.stream()))
-    return y_pair
-
-
 def rq_coupling_final_supported(num_bins, tails, hidden, lda):
     return bool(N.load().nfk_rq_coupling_final_supported(int(num_bins), 1 if tails == "linear" else 0, int(hidden), int(lda)))
 

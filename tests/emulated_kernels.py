@@ -284,7 +284,6 @@ def install(monkeypatch):
             segment_sum_=segment_sum_, f16x3_supported=f16x3_supported, linear_f16x3=linear_f16x3,
             rq_coupling_final_supported=rq_coupling_final_supported, rq_coupling_final_padded_params=rq_coupling_final_padded_params,
             rq_coupling_final=rq_coupling_final, affine_coupling_final=affine_coupling_final, affine_coupling_rows=affine_coupling_rows,
-            rq_coupling_step_supported=rq_coupling_step_supported, rq_coupling_step=rq_coupling_step,
-            residual_trunk_supported=lambda *a: False).items():
+            rq_coupling_step_supported=rq_coupling_step_supported, rq_coupling_step=rq_coupling_step).items():
         monkeypatch.setattr(K, name, fn)
     return calls

@@ -27,7 +27,7 @@ def test_library_exports_every_symbol():
     for name in declared_functions():
         assert hasattr(lib, name), name
     loaded = _native.load()
-    assert loaded.nfk_version() == 4
+    assert loaded.nfk_version() == 5
     assert loaded.nfk_launch_count() >= 0
 
 
