@@ -393,10 +393,7 @@ def run_native(args):
 
     ms_per_step = ms_total / args.steps
     value = world * rows / (ms_per_step * 1e-3)
-    config = workload_config(args, world)
-    config.update({"peaks": peaks["source"],
-                   "arithmetic": "fp32 in / fp32 out; dense layers multiply fp16 (hi,lo) split pairs with 3 tcgen05 kind::f16 "
-                                 "MMAs per product (22-bit operands) and accumulate in fp32"})
+    config = workload_config(args, world)          # identical in the reference arm's line
     result = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
@@ -405,6 +402,9 @@ def run_native(args):
         "e2e": {"value": world * rows / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": rows * FEATURES * 4,
                 "d2h_bytes_per_step": int(out.numel()) * 4, "ms_per_step": e2e_ms, "steps": e2e_steps},
         "tflops_effective": FLOP_PER_SAMPLE * value / 1e12,
+        "notes": {"peaks": peaks["source"],
+                  "arithmetic": "fp32 in / fp32 out; dense layers multiply fp16 (hi,lo) split pairs with 3 tcgen05 kind::f16 MMAs "
+                                "per product (22-bit operands) and accumulate in fp32"},
     }
     # ---- parity of the timed result: random rows of the batch just timed against the CPU oracle -----------------------------
     if not args.no_parity_check:
