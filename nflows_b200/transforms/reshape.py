@@ -1,6 +1,5 @@
 """SqueezeTransform (reference nflows/transforms/reshape.py:7-68): space-to-depth with a 2x2 (factor x factor) window,
 the RealNVP "squeeze".  Pure index shuffling (log|det| = 0)."""
-import torch
 
 from ..utils import typechecks as check
 from .base import Transform

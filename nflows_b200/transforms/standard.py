@@ -1,5 +1,4 @@
 """Trivial transforms kept for API compatibility (reference nflows/transforms/standard.py:12-90); plain torch."""
-import numpy as np
 import torch
 
 from .base import Transform
