@@ -58,7 +58,7 @@ def test_kernel_source_matches_reference_distribution(host_lib, lean):
                 for q in (0.5, 0.99, 0.999):
                     i = min(n - 1, int(q * n))
                     assert e[i] <= 2 * r[i] + 1e-5, (name, inv, q, float(e[i]), float(r[i]))
-                assert e[-1] <= 30 * r[-1] + 1e-5
+                assert e[-1] <= 15 * r[-1] + 1e-5          # as on the GPU (profiles/parity_calibration_r2.txt: largest observed ratio 10.1)
 
 
 def test_kernel_source_identity_and_domain_flag(host_lib):
@@ -97,3 +97,23 @@ def test_lean_form_agrees_with_the_scan_form(host_lib, bins):
             assert ey[i99] <= 2e-6 and el[i99] <= 2e-5, (bins, tails, inv, float(ey[i99]), float(el[i99]))
             # a knot within one rounding of x may put the two forms in neighbouring bins: same spline, same value to ~1e-5
             assert ey[-1] <= 5e-5, (bins, tails, inv, float(ey[-1]))
+
+
+def test_lean_form_inverse_is_the_inverse_of_its_forward(host_lib):
+    """Round trip of the kernel's own spline source: inverse(forward(x)) = x and the two log-determinants cancel, for every
+    bin count the fused kernels are instantiated for, moderately sharp parameters, both tail modes."""
+    for bins in (4, 8, 10, 16):
+        torch.manual_seed(100 + bins)
+        n = 3000
+        uw, uh = torch.randn(n, bins) * 1.5, torch.randn(n, bins) * 1.5
+        for tails in ("linear", None):
+            ud = torch.randn(n, bins - 1 if tails else bins + 1)
+            desc = spline_desc(bins, tails, 3.0, 0, 1, 0, 1, 1e-3, 1e-3, 1e-3, False, 2.0)
+            x = torch.randn(n) * 2.5 if tails else torch.rand(n)
+            y, lad, f = run(host_lib, desc, False, x, uw, uh, ud, lean=True)
+            back, lad_back, f2 = run(host_lib, desc, True, y, uw, uh, ud, lean=True)
+            assert f == 0 and f2 == 0
+            e = errs(back, x)
+            assert e[int(0.999 * n)] <= 2e-5 and e[-1] <= 2e-3, (bins, tails, float(e[int(0.999 * n)]), float(e[-1]))
+            el = errs(lad_back, -lad)
+            assert el[int(0.99 * n)] <= 2e-4, (bins, tails, float(el[int(0.99 * n)]))
